@@ -1,0 +1,290 @@
+"""Per-replica trainer + job driver.
+
+Parity targets (reference, read-only):
+  * ``train_rnn(partition, net_settings, FLAGS, train_optimizer)``   /root/reference/src/rnn.py:180-297
+  * standalone ``train_rnn(dataset, net_settings, train_optimizer)`` /root/reference/src/lstm-no-spark.py:153-251
+  * driver ``main``                                                    /root/reference/src/rnn.py:339-411
+
+One implementation serves both entry points.  Differences by design: the cross-replica mean
+is exact and is written back into every replica and to ``--output_path`` (Q1, Q12); one run timestamp is
+shared by all ranks; a real resume path exists (Q4); replicas start from identical seeded weights unless
+``--independent_init`` (Q9).
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import data as D
+from .config import Config
+from .models.classifier import SequenceClassifier
+from .models.recurrent.lstm import clear_weight_decay_collection
+from .ops import functional as F
+from .ops.loss import compute_accuracy, compute_loss
+from .ops.optim import FlatOptimizer
+from .parallel.comm import Communicator, make_communicator
+from .utils import checkpoint as ckpt
+from .utils import metrics as M
+
+try:
+    from tqdm import trange
+except Exception:                                    # pragma: no cover
+    trange = None
+
+
+def resolve_device(cfg: Config, rank: int) -> torch.device:
+    if cfg.device == "cpu" or (cfg.device == "auto" and not torch.cuda.is_available()):
+        return torch.device("cpu")
+    n = torch.cuda.device_count()
+    if n == 0:
+        raise RuntimeError("--device cuda requested but no GPU is visible")
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    if local >= n:
+        raise RuntimeError(f"--partitions needs {local + 1} GPUs, only {n} visible (Q14: one rank per GPU)")
+    torch.cuda.set_device(local)
+    return torch.device("cuda", local)
+
+
+def resolve_dtype(cfg: Config, device: torch.device) -> torch.dtype:
+    if cfg.dtype == "auto":
+        return torch.bfloat16 if device.type == "cuda" else torch.float32
+    return {"fp32": torch.float32, "float32": torch.float32, "bf16": torch.bfloat16, "bfloat16": torch.bfloat16}[cfg.dtype]
+
+
+def compute_max_steps(cfg: Config, batch_size: int, per_epoch: int) -> int:
+    if cfg.max_steps:
+        return cfg.max_steps
+    if cfg.steps_mode == "compat":
+        return cfg.epochs * (batch_size if batch_size else 1)      # src/rnn.py:256 (sic), Q5
+    return cfg.epochs * per_epoch
+
+
+class ReplicaResult(dict):
+    pass
+
+
+def train_rnn(partition, cfg: Config, rank: int = 0, world_size: int = 1, comm: Optional[Communicator] = None,
+              train_optimizer: Optional[Callable] = None, standalone: bool = False,
+              run_stamp: Optional[str] = None) -> Optional[ReplicaResult]:
+    """Train one replica on one shard.  ``partition`` = ``(key, rows)`` (distributed) or a list of rows
+    (standalone) or ``(key, (x ndarray, y ndarray))`` for pre-parsed / synthetic data."""
+    comm = comm or Communicator(0, 1)
+    prefix_name = "lstm_no_spark" if standalone else "spark_lstm"
+    tag = "RNN-LSTM"
+
+    if partition is None or (isinstance(partition, (list, tuple)) and len(partition) == 0):
+        print(f"{tag} - ZERO SIZE")
+        return None
+    if standalone and not (isinstance(partition, tuple) and len(partition) == 2 and isinstance(partition[0], int)):
+        partition_key, rows = 0, partition
+    else:
+        partition_key, rows = partition
+    if not cfg.quiet:
+        print(f"LSTM - Partition: {partition_key}")
+
+    device = resolve_device(cfg, rank)
+    dtype = resolve_dtype(cfg, device)
+    F.set_backend(cfg.backend if cfg.backend != "auto" else "auto")
+
+    if isinstance(rows, tuple):
+        train_x, train_y = rows
+    else:
+        train_x, train_y = D.process_batch(rows, normalize=cfg.normalize, seq_len=cfg.seq_len,
+                                           in_features=cfg.in_features)
+    batch_size = D.resolve_batch_size(cfg.batch_size, train_x.shape[0])
+
+    # ---- model -------------------------------------------------------------------------------------
+    clear_weight_decay_collection()
+    seed = cfg.seed + (1000003 * (rank + 1) if cfg.independent_init else 0)
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(seed)
+    model = SequenceClassifier(cfg, batch_size=batch_size, device="cpu", generator=gen)
+    model.to(device)
+    model.build_flat()
+    comm.adopt(model.flat)
+    model.set_compute_dtype(dtype)
+    make_opt = train_optimizer(cfg.learning_rate) if train_optimizer is not None else None
+    if make_opt is not None:
+        optimizer = make_opt(model.flat)
+    else:
+        optimizer = FlatOptimizer(model.flat, cfg.learning_rate, cfg.optimizer)
+
+    # ---- run directory -----------------------------------------------------------------
+    current_exec = run_stamp or str(time.time())
+    model_save_dir = os.path.join(cfg.checkpoint_path, current_exec) if standalone else \
+        os.path.join(cfg.checkpoint_path, current_exec, str(partition_key))
+    saver = ckpt.Saver(model_save_dir, prefix_name)
+    saver.write_params_settings(cfg.params_str())
+    sink = M.SummarySink(os.path.join(model_save_dir, "train"))
+    jlog = M.JsonLog(cfg.json_log)
+
+    start_step = 0
+    if cfg.resume or cfg.use_pretrained_model:
+        src = cfg.resume or ckpt.find_latest_run(cfg.checkpoint_path, None if standalone else str(partition_key))
+        if src and os.path.isdir(src):
+            src = ckpt.latest_checkpoint(src)
+        if src:
+            variables, meta, opt_state = ckpt.load(src)
+            model.load_reference_state_dict(variables, strict=False)
+            if opt_state is not None:
+                optimizer.load_state_dict(opt_state["optimizer"])
+            start_step = int(meta.get("global_step", -1)) + 1
+            if not cfg.quiet:
+                print(f"{tag} - restored {src} (resuming at step {start_step})")
+
+    loader = D.DeviceShard(train_x, train_y, batch_size, device, dtype=torch.float32, shuffle=True,
+                           seed=cfg.seed + 17 * (rank + 1))
+    max_steps = compute_max_steps(cfg, batch_size, loader.per_epoch)
+
+    use_bar = (trange is not None) and (rank == 0) and not cfg.quiet
+    total_steps = trange(start_step, max_steps) if use_bar else range(start_step, max_steps)
+
+    prof = None
+    if cfg.trace and rank == 0:
+        acts = [torch.profiler.ProfilerActivity.CPU]
+        if device.type == "cuda":
+            acts.append(torch.profiler.ProfilerActivity.CUDA)
+        prof = torch.profiler.profile(activities=acts)
+        prof.__enter__()
+
+    fault = None
+    if cfg.fault_inject:
+        fr, fs = cfg.fault_inject.split(":")
+        fault = (int(fr), int(fs))
+
+    timer = M.DeviceTimer(device)
+    start = time.time()
+    timer.start()
+    t_acc, t_loss = 0.0, 0.0
+    samples = 0
+    for step in total_steps:
+        if fault is not None and fault == (rank, step):
+            sys.stderr.write(f"{tag} - fault injected on rank {rank} at step {step}\n")
+            sys.stderr.flush()
+            os._exit(17)
+        train_input, train_labels = loader.next()
+
+        with M.nvtx_range("fwd_bwd", cfg.nvtx):
+            model.flat.zero_grad()
+            loss, _logits, _correct = model(train_input, train_labels)
+            if cfg.weight_decay:
+                from .models.recurrent.lstm import weight_decay_terms
+                loss = loss + torch.stack(weight_decay_terms()).sum()
+            loss.backward()
+        with M.nvtx_range("update", cfg.nvtx):
+            if cfg.sync_mode == "grad_allreduce" and world_size > 1:
+                comm.grad_step_(model.flat, optimizer)
+            else:
+                optimizer.step()
+        samples += batch_size
+
+        if cfg.sync_mode == "param_avg" and cfg.sync_every and world_size > 1 and (step + 1) % cfg.sync_every == 0:
+            with M.nvtx_range("param_avg", cfg.nvtx):
+                comm.average_params_(model.flat, cfg.average_scope)
+
+        is_eval = (step % cfg.evaluate_every == 0) or (step + 1) == max_steps
+        if use_bar or is_eval:
+            t_loss = float(loss.detach().float().item())
+        if use_bar:
+            total_steps.set_description("Loss: {:.4f} - t_acc {:.3f}".format(t_loss, t_acc))
+
+        if is_eval:
+            with M.nvtx_range("eval_ckpt", cfg.nvtx):
+                saver.save(model.reference_state_dict(), global_step=step,
+                           extra={"rank": rank, "world_size": world_size, "partition_key": partition_key,
+                                  "loss": t_loss, "config": cfg.__dict__},
+                           opt_state={"optimizer": optimizer.state_dict(), "loader": loader.state_dict()})
+                with torch.no_grad(), M.capture(sink):
+                    h = model.features(train_input)      # same batch, from the initial state (src/rnn.py:276-279)
+                    logits = model.head(h)
+                    e_loss = compute_loss(labels=train_labels, logits=logits)
+                    e_acc = compute_accuracy(labels=train_labels, logits=logits)
+                t_loss, t_acc = float(e_loss.item()), float(e_acc.item())
+                sink.flush(step)
+                jlog.write(step=step, loss=t_loss, acc=t_acc, rank=rank)
+            if use_bar:
+                total_steps.set_description("Loss: {:.4f} - t_acc {:.3f}".format(t_loss, t_acc))
+
+    # ---- the cross-replica average (src/rnn.py:393-407) ------------------------------------------------
+    if world_size > 1 and cfg.sync_mode == "param_avg":
+        with M.nvtx_range("final_param_avg", cfg.nvtx):
+            comm.average_params_(model.flat, cfg.average_scope)
+    device_ms = timer.stop_ms()
+    end_time = time.time() - start
+    n_steps = max(1, max_steps - start_step)
+    if not cfg.quiet:
+        print("{} - Partition: {} - Time: {}s".format(tag, partition_key, end_time))
+    if prof is not None:
+        prof.__exit__(None, None, None)
+        prof.export_chrome_trace(cfg.trace)
+
+    records = [(k, [[t.detach().float().cpu().clone() for t in layer] if isinstance(layer, list)
+                    else layer.detach().float().cpu().clone() for layer in v])
+               for k, v in model.rnn.map_data_by_key()]
+    result = ReplicaResult(partition_key=partition_key, rank=rank, records=records,
+                           variables=model.reference_state_dict(), loss=t_loss, acc=t_acc, steps=n_steps,
+                           seconds=end_time, device_ms=device_ms, samples=samples, model_save_dir=model_save_dir)
+    jlog.write(event="done", rank=rank, seconds=end_time, device_ms=device_ms, samples_per_s=samples / max(end_time, 1e-9))
+    sink.close()
+    jlog.close()
+    return result
+
+
+# ====================================================================================================
+# job driver
+# ====================================================================================================
+def _rank_main(rank: int, world_size: int, cfg: Config, shards, standalone: bool):
+    device = resolve_device(cfg, rank)
+    comm = make_communicator(cfg.comm, rank, world_size, device, cfg.timeout_s)
+    try:
+        stamp = comm.broadcast_object(str(time.time()), src=0)
+        shard = shards[rank] if shards is not None else None
+        res = train_rnn(shard, cfg, rank, world_size, comm, standalone=standalone, run_stamp=stamp)
+        comm.barrier()
+        if res is not None and rank != 0:
+            # only rank 0's records are needed by the driver (all replicas hold the same average)
+            res = ReplicaResult({k: v for k, v in res.items() if k not in ("records", "variables")})
+        return res
+    finally:
+        comm.close()
+
+
+def load_shards(cfg: Config, world_size: int, standalone: bool):
+    if cfg.synthetic:
+        n_per = cfg.synthetic // world_size
+        shards = []
+        for r in range(world_size):
+            x, y = D.synthetic_sequences(n_per, cfg.seq_len, cfg.in_features, cfg.num_classes, seed=cfg.seed + r)
+            shards.append((r, (x, y)))
+        return shards
+    if standalone:
+        return [(0, D.read_dataset_from_path(cfg.training_path))]
+    return D.text_to_partitions(cfg.training_path, world_size, shuffle=True, seed=cfg.seed, remainder=cfg.remainder)
+
+
+def run_job(cfg: Config, standalone: bool = False) -> Dict:
+    """``main`` of both entry points: shard -> N replicas -> average -> output."""
+    from .parallel.launch import launch, in_torchrun
+    world_size = 1 if standalone else cfg.partitions
+    if in_torchrun():
+        world_size = int(os.environ["WORLD_SIZE"])
+    if not cfg.quiet:
+        print("Total workers: ", f"[{world_size}]")
+    shards = load_shards(cfg, world_size, standalone)
+    start = time.time()
+    results = launch(_rank_main, world_size, args=(cfg, shards, standalone))
+    total = time.time() - start
+    res0 = next((r for r in results if r is not None and "records" in r), None)
+    if res0 is not None and cfg.output_path:
+        ckpt.save_averaged_model(cfg.output_path, res0["records"], res0["variables"],
+                                 {"world_size": world_size, "sync_mode": cfg.sync_mode, "average_scope": cfg.average_scope,
+                                  "hidden_units": cfg.hidden_units, "seconds": total})
+    if not cfg.quiet:
+        print("RNN-LSTM - Total Processing Time {}s".format(total))
+    return {"results": results, "seconds": total, "world_size": world_size}
