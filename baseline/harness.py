@@ -1,0 +1,88 @@
+"""Stand-in for "the reference's own NCCL(+cuBLAS) build" (SURVEY §6).
+
+The reference (TensorFlow-1.0 + PySpark, /root/reference/src/rnn.py) has no GPU/NCCL code path and cannot run in this
+image, so the bar our kernels are measured against is built here from stock library parts only — none of this
+framework's models, kernels or engine:
+
+    torch.nn.LSTM (cuDNN persistent RNN kernels, cuBLAS GEMMs), bf16 autocast over fp32 master weights
+    torch.nn.Linear head + F.cross_entropy
+    torch.optim.Adam(fused=True)
+    DistributedDataParallel -> NCCL all_reduce of the gradients every step (bucketed, overlapped)
+
+Same model shape, same schedule (per-step gradient allreduce), same synthetic data shapes as bench.py's own arm.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class CudnnLSTMClassifier(nn.Module):
+    def __init__(self, hidden, in_features, num_classes):
+        super().__init__()
+        assert len(set(hidden)) == 1, "nn.LSTM stacks equal-width layers"
+        self.lstm = nn.LSTM(in_features, hidden[0], num_layers=len(hidden), batch_first=True)
+        self.head = nn.Linear(hidden[-1], num_classes)
+
+    def forward(self, x):
+        out, _ = self.lstm(x)
+        return self.head(out[:, -1, :])
+
+
+class BaselineRunner:
+    def __init__(self, hidden, in_features, num_classes, batch, seq_len, rank, world, device, optimizer="adam", lr=1e-3):
+        self.rank, self.world, self.device = rank, world, device
+        self.B, self.T, self.D, self.C = batch, seq_len, in_features, num_classes
+        torch.manual_seed(0)
+        if world > 1 and not dist.is_initialized():
+            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+        model = CudnnLSTMClassifier(hidden, in_features, num_classes).to(device)
+        self.model = nn.parallel.DistributedDataParallel(model, device_ids=[device.index]) if world > 1 else model
+        if optimizer == "adam":
+            self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, fused=True)
+        else:
+            self.opt = torch.optim.SGD(self.model.parameters(), lr=lr)
+
+    def train_step(self, x, y):
+        self.opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = self.model(x)
+        loss = F.cross_entropy(logits.float(), y)
+        loss.backward()
+        self.opt.step()
+        return loss.detach()
+
+    def make_steps(self):
+        B, T, D, C = self.B, self.T, self.D, self.C
+        rng = np.random.default_rng(1234 + self.rank)
+        nb = 4
+        xs = rng.standard_normal((nb * B, T, D), dtype=np.float32)
+        ys = rng.integers(0, C, size=nb * B).astype(np.int64)
+        dev_x = torch.as_tensor(xs).to(self.device, dtype=torch.bfloat16)
+        dev_y = torch.as_tensor(ys).to(self.device)
+        host_x = torch.as_tensor(xs).to(torch.bfloat16).pin_memory()
+        host_y = torch.as_tensor(ys).pin_memory()
+        stage_x = torch.empty(B, T, D, dtype=torch.bfloat16, device=self.device)
+        stage_y = torch.empty(B, dtype=torch.int64, device=self.device)
+        loss_host = torch.empty((), dtype=torch.float32, pin_memory=True)
+        it = {"i": 0}
+
+        def step_dev():
+            i = it["i"] % nb
+            it["i"] += 1
+            return self.train_step(dev_x[i * B:(i + 1) * B], dev_y[i * B:(i + 1) * B])
+
+        def step_e2e():
+            i = it["i"] % nb
+            it["i"] += 1
+            stage_x.copy_(host_x[i * B:(i + 1) * B], non_blocking=True)
+            stage_y.copy_(host_y[i * B:(i + 1) * B], non_blocking=True)
+            loss = self.train_step(stage_x, stage_y)
+            loss_host.copy_(loss.float())
+            return loss_host
+
+        h2d = B * T * D * 2 + B * 8
+        return step_dev, step_e2e, h2d, 4, 0, {"lstm": "cudnn", "comm": "nccl-ddp" if self.world > 1 else "none"}

@@ -1,0 +1,253 @@
+#!/usr/bin/env python
+"""Headline benchmark (BASELINE.json): samples/sec of the 2-layer-1024 LSTM, seq_len 128, batch 256 per GPU, bf16,
+per-step gradient allreduce, synthetic sequences / random-init weights.
+
+    python bench.py --gpus N --steps K --warmup W [--impl ours|reference|baseline]
+
+N > 1 is launched by the driver under torchrun (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the env), one rank
+per GPU.  Rank 0 prints ONE JSON line.  ``value`` is the whole-job aggregate (sum over GPUs); timing is CUDA events
+on the launching stream bracketed by barrier + synchronize, max over ranks.
+
+  --impl ours       this framework through its public API (lstm_tensorspark_b200.engine.TrainEngine)
+  --impl reference  the unmodified reference from baseline/_ref — it is Python-2 / TF-1.0 / PySpark source without
+                    packaging metadata and cannot be installed here (DESIGN.md §Reference arm) -> "unavailable"
+  --impl baseline   our stand-in for "the reference's own NCCL(+cuBLAS) build" (BASELINE.md §2): cuDNN nn.LSTM +
+                    NCCL all_reduce + torch fused Adam, same model / schedule (baseline/harness.py)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL = dict(hidden_units="1024,1024", in_features=1024, seq_len=128, batch_size=256, num_classes=10)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "baseline"])
+    ap.add_argument("--comm", default="auto", help="ours: fused (default for N>1) | nccl")
+    ap.add_argument("--optimizer", default="adam")
+    ap.add_argument("--cuda_graph", type=int, default=0)
+    ap.add_argument("--hidden_units", default=MODEL["hidden_units"])
+    ap.add_argument("--in_features", type=int, default=MODEL["in_features"])
+    ap.add_argument("--seq_len", type=int, default=MODEL["seq_len"])
+    ap.add_argument("--batch_size", type=int, default=MODEL["batch_size"])
+    ap.add_argument("--no_e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    return rank, world, local
+
+
+def run_reference(args):
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    why = ("reference is Python-2/TensorFlow-1.0/PySpark source with no setup.py/pyproject (pip install fails: "
+           "'neither setup.py nor pyproject.toml found'); tensorflow and pyspark are not in this image")
+    if os.path.isdir(ref_dir) and any(f.endswith(".py") for _, _, fs in os.walk(ref_dir) for f in fs):
+        why = "reference sources present under baseline/_ref but need python2 + tensorflow 1.0 + pyspark (absent)"
+    rank, _, _ = dist_env()
+    if rank == 0:
+        print(json.dumps({"impl": "reference", "unavailable": why}))
+    return 0
+
+
+def timed_loop(torch, dist, world, device, step_fn, steps, warmup):
+    for _ in range(warmup):
+        step_fn()
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier(device_ids=[device.index])
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step_fn()
+    e1.record()
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier(device_ids=[device.index])
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+    rank, world, local = dist_env()
+    if world != args.gpus and rank == 0 and world > 1:
+        sys.stderr.write(f"[bench] WORLD_SIZE={world} != --gpus {args.gpus}; using WORLD_SIZE\n")
+    n_gpus = world
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29512")
+
+    B, T, D = args.batch_size, args.seq_len, args.in_features
+    C = MODEL["num_classes"]
+    hidden = [int(h) for h in args.hidden_units.split(",")]
+    clocks = ClockSampler(local)
+
+    if args.impl == "baseline":
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import harness
+        runner = harness.BaselineRunner(hidden, D, C, B, T, rank, world, device, optimizer=args.optimizer)
+        step_dev, step_e2e, h2d, d2h, launches, cfg_extra = runner.make_steps()
+        model_name = f"cudnn-lstm-{len(hidden)}x{hidden[0]}"
+        par = f"dp{n_gpus}-nccl"
+    else:
+        from lstm_tensorspark_b200.config import Config
+        from lstm_tensorspark_b200.engine import TrainEngine
+        from lstm_tensorspark_b200.parallel.comm import make_communicator
+        from lstm_tensorspark_b200 import data as Dm
+        from lstm_tensorspark_b200.ops import cuda_lstm
+        comm_kind = args.comm if args.comm != "auto" else "fused"
+        cfg = Config(hidden_units=args.hidden_units, in_features=D, seq_len=T, batch_size=B, num_classes=C,
+                     partitions=world, sync_mode="grad_allreduce", optimizer=args.optimizer, init="scaled",
+                     learn_initial_state=False, comm=comm_kind, dtype="bf16", device="cuda", learning_rate=1e-3, quiet=True)
+        comm = make_communicator(comm_kind if world > 1 else "auto", rank, world, device)
+        eng = TrainEngine(cfg, rank, world, comm, batch_size=B, device=device, dtype=torch.bfloat16)
+        # synthetic shard: 4 distinct device-resident batches (inputs >> L2 together with the activations)
+        nb = 4
+        xs, ys = Dm.synthetic_sequences(nb * B, T, D, C, seed=1234 + rank)
+        dev_x = torch.as_tensor(xs).to(device=device, dtype=torch.bfloat16)
+        dev_y = torch.as_tensor(ys).to(device)
+        it = {"i": 0}
+
+        def step_dev():
+            i = it["i"] % nb
+            it["i"] += 1
+            return eng.step(dev_x[i * B:(i + 1) * B], dev_y[i * B:(i + 1) * B])
+
+        loader = Dm.PinnedHostLoader(xs, ys, B, device, dtype=torch.bfloat16, shuffle=False, seed=rank)
+        loss_host = torch.empty((), dtype=torch.float32, pin_memory=True)
+
+        def step_e2e():
+            x, y = loader.next()                       # pinned host -> device copy of this step's inputs
+            loss = eng.step(x, y)
+            loss_host.copy_(loss.float(), non_blocking=False)    # device -> host read of the result
+            return loss_host
+
+        if args.cuda_graph:
+            eng.capture(dev_x[:B], dev_y[:B])
+        h2d, d2h = loader.bytes_per_batch, 4
+        from lstm_tensorspark_b200.ops import cuda_ext
+        step_dev()
+        k0 = cuda_ext.LAUNCHES["n"]
+        step_dev()
+        torch.cuda.synchronize(device)
+        launches = cuda_ext.LAUNCHES["n"] - k0          # our kernels per step (counted at the binding layer)
+        cfg_extra = {"comm": comm.name, "fast_path": cuda_lstm.STATS["fast_fwd"] > 0, "cuda_graph": bool(args.cuda_graph),
+                     "optimizer": args.optimizer}
+        model_name = f"lstm-{len(hidden)}x{hidden[0]}"
+        par = f"dp{n_gpus}" + ("" if world == 1 else f"-{comm.name}")
+
+    clocks.start()
+    ms = timed_loop(torch, dist, world, device, step_dev, args.steps, args.warmup)
+    clk = clocks.stop()
+    e2e = None
+    if not args.no_e2e:
+        ms_e2e = timed_loop(torch, dist, world, device, step_e2e, args.steps, max(3, args.warmup // 2))
+        e2e = {"value": B * n_gpus * args.steps / (ms_e2e / 1e3), "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+    if args.impl == "ours":
+        cuda_lstm.check_kernel_errors(device)
+        if hasattr(comm, "check_errors"):
+            comm.check_errors()
+
+    value = B * n_gpus * args.steps / (ms / 1e3)
+    out = {"metric": "samples/sec", "value": value, "unit": "samples/s", "n_gpus": n_gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "impl": args.impl,
+           "config": {"model": model_name, "global_batch": B * n_gpus, "per_gpu_batch": B, "seq_len": T, "in_features": D,
+                      "num_classes": C, "parallelism": par, "sync": "per-step gradient allreduce" if n_gpus > 1 else "none",
+                      "l2": "per-step working set (activations+inputs, >1 GB) exceeds the 126 MB L2; 4 rotating input batches",
+                      **cfg_extra},
+           "clocks": clk, "gpu_launches": launches * args.steps}
+    if e2e is not None:
+        out["e2e"] = e2e
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1 and dist.is_initialized():
+        try:
+            dist.destroy_process_group()
+        except Exception:
+            pass
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,223 @@
+#!/usr/bin/env python
+"""GPU bring-up probe: runs every kernel check in its OWN subprocess under a timeout (a faulting kernel poisons
+its CUDA context — it must not take the other checks down) and appends results to gpurun_out/probe.jsonl.
+
+    python bench/gpu_probe.py [check ...]        # no args = all checks
+"""
+from __future__ import annotations
+
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "gpurun_out")
+
+
+def _emit(name, **kw):
+    os.makedirs(OUT, exist_ok=True)
+    rec = {"check": name, **kw}
+    with open(os.path.join(OUT, "probe.jsonl"), "a") as f:
+        f.write(json.dumps(rec, default=str) + "\n")
+    print("PROBE", json.dumps(rec, default=str), flush=True)
+
+
+def _time_ms(fn, iters=10, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+# ---------------------------------------------------------------------------------------------------------
+def check_env():
+    import torch
+    p = torch.cuda.get_device_properties(0)
+    _emit("env", name=p.name, sms=p.multi_processor_count, mem_gb=p.total_memory / 2**30, cc=f"{p.major}.{p.minor}",
+          torch=torch.__version__, n_gpus=torch.cuda.device_count())
+
+
+def check_simple():
+    import torch
+    from lstm_tensorspark_b200.ops.cuda_ext import ext
+    from lstm_tensorspark_b200.ops import reference as ref
+    E = ext()
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    for dt in (torch.float32, torch.bfloat16):
+        B, H = 37, 24
+        pre = torch.randn(B, 4 * H, device=dev).to(dt)
+        bias = torch.randn(4 * H, device=dev)
+        c = torch.randn(B, H, device=dev)
+        h, cn, act = E.lstm_pointwise_fwd(pre, bias, c)
+        i, f, g, o = ref.lstm_gates(pre.float() + bias)
+        c_ref = f * c + i * g
+        h_ref = o * torch.tanh(c_ref)
+        _emit("pointwise_fwd", dtype=str(dt), h_err=float((h.float() - h_ref).abs().max()), c_err=float((cn - c_ref).abs().max()))
+    # head
+    B, H, C = 50, 96, 7
+    hh = torch.randn(B, H, device=dev)
+    W = torch.randn(H, C, device=dev) * 0.1
+    b = torch.randn(C, device=dev)
+    y = torch.randint(0, C, (B,), device=dev)
+    logits, dlog, loss, corr = E.head_xent(hh, W, b, y)
+    lr, lossr, corrr = ref.head_xent(hh, W, b, y)
+    _emit("head_xent", logit_err=float((logits - lr).abs().max()), loss=float(loss / B), loss_ref=float(lossr), correct=int(corr), correct_ref=int(corrr))
+    # adam
+    n = 16384
+    p = torch.randn(n, device=dev); g = torch.randn(n, device=dev); m = torch.zeros(n, device=dev); v = torch.zeros(n, device=dev)
+    p2, m2, v2 = p.clone(), m.clone(), v.clone()
+    sh = torch.empty(n, dtype=torch.bfloat16, device=dev)
+    lr_t = 1e-3 * (1 - 0.999) ** 0.5 / (1 - 0.9)
+    E.flat_adam(p, g, m, v, sh, lr_t, 0.9, 0.999, 1e-8, 0.0, 1.0)
+    ref.adam_step_(p2, g, m2, v2, 1, 1e-3)
+    _emit("flat_adam", p_err=float((p - p2).abs().max()), shadow_err=float((sh.float() - p).abs().max()))
+
+
+def check_gemm():
+    import torch
+    from lstm_tensorspark_b200.ops.cuda_ext import ext
+    E = ext()
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    shapes = [(128, 128, 64), (128, 128, 256), (256, 256, 512), (384, 1024, 1024), (1000, 520, 264), (32768, 4096, 1024)]
+    for variant in (0, 1):
+        for (M, N, K) in shapes:
+            A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+            Bm = (torch.randn(N, K, device=dev) * 0.5).bfloat16()
+            bias = torch.randn(N, device=dev)
+            try:
+                Cc = E.gemm_bf16_tn(A, Bm, bias, True, variant)
+                torch.cuda.synchronize()
+                if M * N <= 4096 * 4096:
+                    R = A.float() @ Bm.float().t() + bias
+                    err = float((Cc - R).abs().max()); rel = err / float(R.abs().max())
+                else:
+                    R = (A[:256].float() @ Bm.float().t() + bias)
+                    err = float((Cc[:256] - R).abs().max()); rel = err / float(R.abs().max())
+                ms = _time_ms(lambda: E.gemm_bf16_tn(A, Bm, None, False, variant))
+                ms_cublas = _time_ms(lambda: A @ Bm.t())
+                _emit("gemm", variant=variant, M=M, N=N, K=K, max_err=err, rel_err=rel, ms=ms, tflops=2.0 * M * N * K / ms / 1e9,
+                      cublas_ms=ms_cublas, cublas_tflops=2.0 * M * N * K / ms_cublas / 1e9)
+            except Exception as e:                # noqa: BLE001
+                _emit("gemm", variant=variant, M=M, N=N, K=K, error=repr(e)[:400])
+                raise
+
+
+def _seq_case(T, B, H, D, check_bwd=True, time_it=False):
+    import torch
+    from lstm_tensorspark_b200.ops import cuda_lstm, reference as ref
+    from lstm_tensorspark_b200.ops.cuda_ext import ext
+    dev = torch.device("cuda")
+    torch.manual_seed(1)
+    x = (torch.randn(T, B, D, device=dev) * 0.5)
+    w_x = (torch.randn(4 * H, D, device=dev) / D ** 0.5)
+    w_h = (torch.randn(4 * H, H, device=dev) / H ** 0.5)
+    bias = torch.randn(4 * H, device=dev) * 0.1
+    h0 = torch.randn(B, H, device=dev) * 0.1
+    c0 = torch.randn(B, H, device=dev) * 0.1
+    params = [x, h0, c0, w_x, w_h, bias]
+    # reference in fp32 on bf16-rounded operands
+    pr = [p.bfloat16().float().requires_grad_(True) if i != 2 else p.clone().requires_grad_(True) for i, p in enumerate(params)]
+    hs_r, hT_r, cT_r = ref.lstm_layer_sequence(*pr)
+    wgt = torch.randn_like(hs_r)
+    (hs_r * wgt).sum().backward()
+    pc = [p.clone().requires_grad_(True) for p in params]
+    xb = pc[0].bfloat16()
+    hs, hT, cT = cuda_lstm.lstm_layer_sequence(xb, pc[1], pc[2], pc[3], pc[4], pc[5])
+    torch.cuda.synchronize()
+    cuda_lstm.check_kernel_errors(dev)
+    out = dict(T=T, B=B, H=H, D=D, fast=cuda_lstm.STATS["fast_fwd"] > 0,
+               h_err=float((hs.float() - hs_r).abs().max()), c_err=float((cT - cT_r).abs().max()), h_ref_max=float(hs_r.abs().max()))
+    if check_bwd:
+        (hs.float() * wgt).sum().backward()
+        torch.cuda.synchronize()
+        cuda_lstm.check_kernel_errors(dev)
+        names = ["dx", "dh0", "dc0", "dw_x", "dw_h", "db"]
+        for n, a, b in zip(names, pc, pr):
+            out[n + "_rel"] = float((a.grad.float() - b.grad).abs().max() / (b.grad.abs().max() + 1e-12))
+    if time_it:
+        E = ext()
+        gx = (xb.reshape(T * B, D) @ w_x.bfloat16().t()).view(T, B, 4 * H).contiguous()
+        whb = w_h.bfloat16().contiguous()
+        ws = cuda_lstm._sync_ws(dev)
+        out["fwd_kernel_ms"] = _time_ms(lambda: E.lstm_seq_fwd(gx, whb, bias, h0.bfloat16(), c0, ws, 0), iters=5, warm=2)
+        out["fwd_us_per_step"] = out["fwd_kernel_ms"] * 1e3 / T
+        hseq, cseq, act = E.lstm_seq_fwd(gx, whb, bias, h0.bfloat16(), c0, ws, 0)
+        whT = whb.t().contiguous()
+        dh = torch.randn(T, B, H, device=dev).bfloat16()
+        z = torch.zeros(B, H, device=dev)
+        out["bwd_kernel_ms"] = _time_ms(lambda: E.lstm_seq_bwd(dh, whT, act, cseq, z, z, ws, 0), iters=5, warm=2)
+        out["bwd_us_per_step"] = out["bwd_kernel_ms"] * 1e3 / T
+        cuda_lstm.check_kernel_errors(dev)
+    _emit("lstm_seq", **out)
+
+
+def check_seq_small():
+    _seq_case(3, 128, 64, 64)
+    _seq_case(5, 100, 128, 72)
+    _seq_case(4, 256, 256, 128)
+
+
+def check_seq_big():
+    _seq_case(16, 256, 1024, 1024, check_bwd=True, time_it=True)
+    _seq_case(128, 256, 1024, 1024, check_bwd=False, time_it=True)
+
+
+def check_generic():
+    os.environ["LSTM_TS_FORCE_GENERIC"] = "1"
+    from lstm_tensorspark_b200.ops import cuda_lstm
+    cuda_lstm.FORCE_GENERIC = True
+    _seq_case(3, 10, 16, 4)
+    _seq_case(6, 33, 48, 20)
+
+
+def check_engine():
+    import torch
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    g.smoke()
+    _emit("smoke", ok=True)
+
+
+def check_iris_gpu():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "lstm-no-spark.py"), "--training_path", os.path.join(ROOT, "dataset/iris.data"),
+                        "--hidden_units", "16", "--epochs", "30", "--checkpoint_path", "/tmp/ck_gpu", "--output_path", "/tmp/out_gpu",
+                        "--quiet"], capture_output=True, text=True, timeout=600)
+    _emit("iris_gpu_standalone", rc=r.returncode, tail=(r.stdout + r.stderr)[-600:])
+
+
+CHECKS = {"env": check_env, "simple": check_simple, "gemm": check_gemm, "generic": check_generic, "seq_small": check_seq_small,
+          "seq_big": check_seq_big, "engine": check_engine, "iris_gpu": check_iris_gpu}
+
+
+def main():
+    if len(sys.argv) >= 3 and sys.argv[1] == "--one":
+        CHECKS[sys.argv[2]]()
+        return 0
+    names = sys.argv[1:] or list(CHECKS)
+    for n in names:
+        t0 = time.time()
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", n], capture_output=True, text=True,
+                               timeout=float(os.environ.get("PROBE_TIMEOUT", "300")))
+            sys.stdout.write(r.stdout[-6000:])
+            if r.returncode != 0:
+                _emit(n + "_FAILED", rc=r.returncode, stderr=r.stderr[-3000:])
+        except subprocess.TimeoutExpired as e:
+            _emit(n + "_TIMEOUT", seconds=time.time() - t0, stdout=(e.stdout or b"")[-2000:] if e.stdout else "")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

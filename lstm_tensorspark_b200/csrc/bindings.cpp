@@ -1,0 +1,232 @@
+// Python bindings for the sm_100a kernels (the only translation unit that sees torch headers).
+// Every function validates device / dtype / contiguity, takes the CURRENT torch CUDA stream (so the kernels
+// are stream-ordered with the rest of the step and capturable in CUDA graphs) and forwards raw pointers to the
+// C-ABI launchers defined next to the kernels.
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <cuda_runtime.h>
+
+#include <optional>
+#include <string>
+#include <vector>
+
+using torch::Tensor;
+
+extern "C" {
+int ts_lstm_pointwise_fwd(const void*, const float*, const float*, void*, float*, void*, int, int, int, cudaStream_t);
+int ts_lstm_pointwise_bwd(const void*, const float*, const float*, const void*, const float*, const float*, void*,
+                          float*, int, int, int, cudaStream_t);
+int ts_head_xent(const void*, const float*, const float*, const long long*, float*, float*, float*, int*, int, int, int,
+                 int, cudaStream_t);
+int ts_xent_rows(const float*, const long long*, float*, float*, int*, int, int, cudaStream_t);
+int ts_flat_adam(float*, const float*, float*, float*, void*, long long, float, float, float, float, float, float,
+                 cudaStream_t);
+int ts_flat_sgd(float*, const float*, void*, long long, float, float, float, cudaStream_t);
+int ts_cast_bf16(const float*, void*, long long, cudaStream_t);
+int ts_fused_allreduce(const unsigned long long*, unsigned long long, unsigned long long, unsigned long long, float*,
+                       float*, unsigned int*, int*, long long, int, int, int, int, int, int, float, float, float, float,
+                       float, double, cudaStream_t);
+int ts_ar_max_blocks();
+int ts_ar_flag_words();
+int ts_gemm_bf16_tn(const void*, const void*, void*, const float*, int, int, int, int, int, int, cudaStream_t);
+int ts_lstm_seq_fwd(const void*, const void*, const float*, const void*, const float*, void*, float*, void*, void*, int,
+                    int, int, unsigned int*, int, cudaStream_t);
+int ts_lstm_seq_bwd(const void*, const void*, const void*, const float*, const void*, float*, float*, void*, void*, int,
+                    int, int, unsigned int*, int, cudaStream_t);
+const char* ts_last_error();
+}
+
+namespace {
+
+void check(int rc, const char* what) {
+  if (rc != 0) {
+    std::string msg = std::string(what) + " failed: rc=" + std::to_string(rc);
+    if (rc > 0) msg += std::string(" (") + cudaGetErrorString((cudaError_t)rc) + ")";
+    const char* le = ts_last_error();
+    if (le && le[0]) msg += std::string(" [") + le + "]";
+    TORCH_CHECK(false, msg);
+  }
+}
+cudaStream_t stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+void chk_cuda(const Tensor& t, const char* n) {
+  TORCH_CHECK(t.is_cuda(), n, " must be a CUDA tensor");
+  TORCH_CHECK(t.is_contiguous(), n, " must be contiguous");
+}
+int is_bf16(const Tensor& t) {
+  TORCH_CHECK(t.scalar_type() == torch::kBFloat16 || t.scalar_type() == torch::kFloat32, "dtype must be bf16 or fp32");
+  return t.scalar_type() == torch::kBFloat16 ? 1 : 0;
+}
+const float* fptr(const std::optional<Tensor>& t) { return t.has_value() ? t->data_ptr<float>() : nullptr; }
+
+// ---- generic LSTM cell epilogue -------------------------------------------------------------------------
+std::vector<Tensor> lstm_pointwise_fwd(const Tensor& pre, const Tensor& bias, const Tensor& c_prev) {
+  chk_cuda(pre, "pre"); chk_cuda(bias, "bias"); chk_cuda(c_prev, "c_prev");
+  c10::cuda::CUDAGuard g(pre.device());
+  int B = pre.size(0), H = pre.size(1) / 4;
+  TORCH_CHECK(bias.scalar_type() == torch::kFloat32 && c_prev.scalar_type() == torch::kFloat32, "bias/c must be fp32");
+  TORCH_CHECK(c_prev.numel() == (int64_t)B * H && bias.numel() == 4 * H, "shape mismatch");
+  auto h = torch::empty({B, H}, pre.options());
+  auto c = torch::empty({B, H}, c_prev.options());
+  auto act = torch::empty_like(pre);
+  check(ts_lstm_pointwise_fwd(pre.data_ptr(), bias.data_ptr<float>(), c_prev.data_ptr<float>(), h.data_ptr(),
+                              c.data_ptr<float>(), act.data_ptr(), B, H, is_bf16(pre), stream()), "lstm_pointwise_fwd");
+  return {h, c, act};
+}
+
+std::vector<Tensor> lstm_pointwise_bwd(const std::optional<Tensor>& dh_a, const std::optional<Tensor>& dh_b,
+                                       const std::optional<Tensor>& dc_in, const Tensor& act, const Tensor& c_prev,
+                                       const Tensor& c_new) {
+  chk_cuda(act, "act"); chk_cuda(c_prev, "c_prev"); chk_cuda(c_new, "c_new");
+  c10::cuda::CUDAGuard g(act.device());
+  int B = act.size(0), H = act.size(1) / 4;
+  if (dh_a.has_value()) { chk_cuda(*dh_a, "dh_a"); TORCH_CHECK(dh_a->scalar_type() == act.scalar_type(), "dh_a dtype"); }
+  if (dh_b.has_value()) { chk_cuda(*dh_b, "dh_b"); TORCH_CHECK(dh_b->scalar_type() == torch::kFloat32, "dh_b fp32"); }
+  if (dc_in.has_value()) { chk_cuda(*dc_in, "dc_in"); TORCH_CHECK(dc_in->scalar_type() == torch::kFloat32, "dc fp32"); }
+  auto dpre = torch::empty_like(act);
+  auto dc = torch::empty_like(c_prev);
+  check(ts_lstm_pointwise_bwd(dh_a.has_value() ? dh_a->data_ptr() : nullptr, fptr(dh_b), fptr(dc_in), act.data_ptr(),
+                              c_prev.data_ptr<float>(), c_new.data_ptr<float>(), dpre.data_ptr(), dc.data_ptr<float>(),
+                              B, H, is_bf16(act), stream()), "lstm_pointwise_bwd");
+  return {dpre, dc};
+}
+
+// ---- head ---------------------------------------------------------------------------------------------------
+std::vector<Tensor> head_xent(const Tensor& h, const Tensor& W, const Tensor& bias, const Tensor& labels) {
+  chk_cuda(h, "h"); chk_cuda(W, "W"); chk_cuda(bias, "bias"); chk_cuda(labels, "labels");
+  c10::cuda::CUDAGuard g(h.device());
+  int B = h.size(0), H = h.size(1), C = W.size(1);
+  TORCH_CHECK(W.size(0) == H && W.scalar_type() == torch::kFloat32 && bias.scalar_type() == torch::kFloat32, "head W/b");
+  TORCH_CHECK(labels.scalar_type() == torch::kInt64 && labels.numel() == B, "labels int64 [B]");
+  auto fo = torch::TensorOptions().device(h.device()).dtype(torch::kFloat32);
+  auto logits = torch::empty({B, C}, fo), dlogits = torch::empty({B, C}, fo);
+  auto loss = torch::zeros({1}, fo);
+  auto correct = torch::zeros({1}, fo.dtype(torch::kInt32));
+  check(ts_head_xent(h.data_ptr(), W.data_ptr<float>(), bias.data_ptr<float>(), (const long long*)labels.data_ptr<int64_t>(),
+                     logits.data_ptr<float>(), dlogits.data_ptr<float>(), loss.data_ptr<float>(), correct.data_ptr<int>(),
+                     B, H, C, is_bf16(h), stream()), "head_xent");
+  return {logits, dlogits, loss, correct};
+}
+
+std::vector<Tensor> xent_rows(const Tensor& logits, const Tensor& labels) {
+  chk_cuda(logits, "logits"); chk_cuda(labels, "labels");
+  c10::cuda::CUDAGuard g(logits.device());
+  TORCH_CHECK(logits.scalar_type() == torch::kFloat32 && labels.scalar_type() == torch::kInt64, "dtypes");
+  int B = logits.size(0), C = logits.size(1);
+  auto dlogits = torch::empty_like(logits);
+  auto loss = torch::zeros({1}, logits.options());
+  auto correct = torch::zeros({1}, logits.options().dtype(torch::kInt32));
+  check(ts_xent_rows(logits.data_ptr<float>(), (const long long*)labels.data_ptr<int64_t>(), dlogits.data_ptr<float>(),
+                     loss.data_ptr<float>(), correct.data_ptr<int>(), B, C, stream()), "xent_rows");
+  return {dlogits, loss, correct};
+}
+
+// ---- optimizer ----------------------------------------------------------------------------------------------
+void flat_adam(Tensor p, const Tensor& g, Tensor m, Tensor v, std::optional<Tensor> shadow, double lr_t, double b1,
+               double b2, double eps, double wd, double gscale) {
+  chk_cuda(p, "p"); chk_cuda(g, "g"); chk_cuda(m, "m"); chk_cuda(v, "v");
+  c10::cuda::CUDAGuard gd(p.device());
+  TORCH_CHECK(p.numel() == g.numel() && p.numel() == m.numel() && p.numel() == v.numel(), "numel mismatch");
+  check(ts_flat_adam(p.data_ptr<float>(), g.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(),
+                     shadow.has_value() ? shadow->data_ptr() : nullptr, p.numel(), lr_t, b1, b2, eps, wd, gscale, stream()),
+        "flat_adam");
+}
+void flat_sgd(Tensor p, const Tensor& g, std::optional<Tensor> shadow, double lr, double wd, double gscale) {
+  chk_cuda(p, "p"); chk_cuda(g, "g");
+  c10::cuda::CUDAGuard gd(p.device());
+  check(ts_flat_sgd(p.data_ptr<float>(), g.data_ptr<float>(), shadow.has_value() ? shadow->data_ptr() : nullptr,
+                    p.numel(), lr, wd, gscale, stream()), "flat_sgd");
+}
+void cast_bf16(const Tensor& p, Tensor shadow) {
+  chk_cuda(p, "p"); chk_cuda(shadow, "shadow");
+  c10::cuda::CUDAGuard gd(p.device());
+  TORCH_CHECK(shadow.scalar_type() == torch::kBFloat16 && shadow.numel() == p.numel(), "shadow");
+  check(ts_cast_bf16(p.data_ptr<float>(), shadow.data_ptr(), p.numel(), stream()), "cast_bf16");
+}
+
+// ---- fused allreduce ----------------------------------------------------------------------------------------
+// ptrs: CPU int64 [4, world] (in, param, shadow, flags); mc_*: multicast addresses or 0.
+void fused_allreduce(const Tensor& ptrs, int64_t mc_in, int64_t mc_param, int64_t mc_shadow, std::optional<Tensor> m,
+                     std::optional<Tensor> v, Tensor epochs, Tensor err, int64_t n, int64_t rank, int64_t world,
+                     int64_t mode, bool two_shot, bool multicast, int64_t blocks, double lr, double b1, double b2,
+                     double eps, double wd, double timeout_s) {
+  TORCH_CHECK(!ptrs.is_cuda() && ptrs.scalar_type() == torch::kInt64 && ptrs.numel() == 4 * world, "ptrs: cpu int64 [4,world]");
+  chk_cuda(epochs, "epochs"); chk_cuda(err, "err");
+  c10::cuda::CUDAGuard gd(epochs.device());
+  check(ts_fused_allreduce((const unsigned long long*)ptrs.data_ptr<int64_t>(), (unsigned long long)mc_in,
+                           (unsigned long long)mc_param, (unsigned long long)mc_shadow,
+                           m.has_value() ? m->data_ptr<float>() : nullptr, v.has_value() ? v->data_ptr<float>() : nullptr,
+                           (unsigned int*)epochs.data_ptr<int>(), err.data_ptr<int>(), n, (int)rank, (int)world, (int)mode,
+                           two_shot ? 1 : 0, multicast ? 1 : 0, (int)blocks, lr, b1, b2, eps, wd, timeout_s, stream()),
+        "fused_allreduce");
+}
+
+// ---- tcgen05 GEMM: C[M,N] = A[M,K] * B[N,K]^T (+bias[N]) ; bf16 in, fp32 accumulate in TMEM --------------------
+Tensor gemm_bf16_tn(const Tensor& A, const Tensor& B, const std::optional<Tensor>& bias, bool out_fp32, int64_t variant) {
+  chk_cuda(A, "A"); chk_cuda(B, "B");
+  c10::cuda::CUDAGuard gd(A.device());
+  TORCH_CHECK(A.scalar_type() == torch::kBFloat16 && B.scalar_type() == torch::kBFloat16, "A/B must be bf16");
+  TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && A.size(1) == B.size(1), "A [M,K], B [N,K]");
+  int M = A.size(0), K = A.size(1), N = B.size(0);
+  auto C = torch::empty({M, N}, A.options().dtype(out_fp32 ? torch::kFloat32 : torch::kBFloat16));
+  check(ts_gemm_bf16_tn(A.data_ptr(), B.data_ptr(), C.data_ptr(), fptr(bias), M, N, K, out_fp32 ? 1 : 0, (int)variant,
+                        A.device().index(), stream()), "gemm_bf16_tn");
+  return C;
+}
+
+// ---- persistent tcgen05 LSTM sequence kernels ------------------------------------------------------------------
+// gx [T,B,4H] bf16 (x·Wx^T, no bias), w_h [4H,H] bf16, bias fp32 [4H], h0 bf16 [B,H], c0 fp32 [B,H]
+// -> h_seq [T+1,B,H] bf16 (row 0 = h0), c_seq [T+1,B,H] fp32, act [T,B,4H] bf16
+std::vector<Tensor> lstm_seq_fwd(const Tensor& gx, const Tensor& w_h, const Tensor& bias, const Tensor& h0,
+                                 const Tensor& c0, Tensor sync_ws, int64_t variant) {
+  chk_cuda(gx, "gx"); chk_cuda(w_h, "w_h"); chk_cuda(bias, "bias"); chk_cuda(h0, "h0"); chk_cuda(c0, "c0");
+  c10::cuda::CUDAGuard gd(gx.device());
+  int T = gx.size(0), B = gx.size(1), H = gx.size(2) / 4;
+  auto h_seq = torch::empty({T + 1, B, H}, gx.options());
+  auto c_seq = torch::empty({T + 1, B, H}, c0.options());
+  auto act = torch::empty({T, B, 4 * H}, gx.options());
+  h_seq[0].copy_(h0);
+  c_seq[0].copy_(c0);
+  sync_ws.narrow(0, 0, 16).zero_();       // step counters restart at 0 every launch; [63] = sticky error flag
+  check(ts_lstm_seq_fwd(gx.data_ptr(), w_h.data_ptr(), bias.data_ptr<float>(), h_seq.data_ptr(), c_seq.data_ptr<float>(),
+                        act.data_ptr(), nullptr, nullptr, nullptr, T, B, H, (unsigned int*)sync_ws.data_ptr<int>(),
+                        (int)variant, stream()), "lstm_seq_fwd");
+  return {h_seq, c_seq, act};
+}
+
+// dh_seq [T,B,H] bf16 (grad wrt every h_t from above), w_hT [H,4H] bf16 (transposed recurrent weights),
+// act/c_seq from forward, dhT fp32 [B,H] / dcT fp32 [B,H] extra grads into the final state (may be zeros)
+// -> dpre [T,B,4H] bf16, dh0 fp32 [B,H], dc0 fp32 [B,H]
+std::vector<Tensor> lstm_seq_bwd(const Tensor& dh_seq, const Tensor& w_hT, const Tensor& act, const Tensor& c_seq,
+                                 const Tensor& dhT, const Tensor& dcT, Tensor sync_ws, int64_t variant) {
+  chk_cuda(dh_seq, "dh_seq"); chk_cuda(w_hT, "w_hT"); chk_cuda(act, "act"); chk_cuda(c_seq, "c_seq");
+  c10::cuda::CUDAGuard gd(act.device());
+  int T = act.size(0), B = act.size(1), H = act.size(2) / 4;
+  auto dpre = torch::empty_like(act);
+  auto dh0 = dhT.clone();
+  auto dc0 = dcT.clone();
+  sync_ws.narrow(0, 0, 16).zero_();
+  check(ts_lstm_seq_bwd(dh_seq.data_ptr(), w_hT.data_ptr(), act.data_ptr(), c_seq.data_ptr<float>(), dpre.data_ptr(),
+                        dh0.data_ptr<float>(), dc0.data_ptr<float>(), nullptr, nullptr, T, B, H,
+                        (unsigned int*)sync_ws.data_ptr<int>(), (int)variant, stream()), "lstm_seq_bwd");
+  return {dpre, dh0, dc0};
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "lstm_tensorspark_b200 sm_100a kernels";
+  m.def("lstm_pointwise_fwd", &lstm_pointwise_fwd);
+  m.def("lstm_pointwise_bwd", &lstm_pointwise_bwd);
+  m.def("head_xent", &head_xent);
+  m.def("xent_rows", &xent_rows);
+  m.def("flat_adam", &flat_adam);
+  m.def("flat_sgd", &flat_sgd);
+  m.def("cast_bf16", &cast_bf16);
+  m.def("fused_allreduce", &fused_allreduce);
+  m.def("ar_max_blocks", []() { return ts_ar_max_blocks(); });
+  m.def("ar_flag_words", []() { return ts_ar_flag_words(); });
+  m.def("gemm_bf16_tn", &gemm_bf16_tn);
+  m.def("lstm_seq_fwd", &lstm_seq_fwd);
+  m.def("lstm_seq_bwd", &lstm_seq_bwd);
+}

@@ -1,0 +1,91 @@
+// Generic-shape LSTM cell epilogue kernels (any B, H): gate activations + c/h update (forward) and the
+// gate-gradient math (backward), each ONE launch per time step instead of the reference's ~19 elementwise
+// TF ops per layer per step (reference: /root/reference/src/models/recurrent/lstm.py:93-109, K3-K7 in SURVEY §2.5).
+// The 4-gate GEMM that feeds them is a library GEMM on this path; shapes that fit the tensor-core tiling
+// take the persistent tcgen05 kernel in lstm_seq_tcgen05.cu instead.
+//
+// Layout: pre/act/dpre are [B, 4H] with column n = 4*j + g, g: 0=i 1=f 2=g(candidate) 3=o. c is fp32.
+#include "ts_common.cuh"
+
+namespace {
+
+template <typename T, bool kFast>
+__global__ void lstm_pointwise_fwd_kernel(const T* __restrict__ pre, const float* __restrict__ bias,
+                                          const float* __restrict__ c_prev, T* __restrict__ h_out,
+                                          float* __restrict__ c_out, T* __restrict__ act, int B, int H) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * H) return;
+  int j = idx % H;
+  const T* p = pre + (size_t)idx * 4;
+  float pi = ts::Cvt<T>::to_f(p[0]) + bias[4 * j + 0];
+  float pf = ts::Cvt<T>::to_f(p[1]) + bias[4 * j + 1];
+  float pg = ts::Cvt<T>::to_f(p[2]) + bias[4 * j + 2];
+  float po = ts::Cvt<T>::to_f(p[3]) + bias[4 * j + 3];
+  float i, f, g, o;
+  if (kFast) {
+    i = ts::sigmoidf_fast(pi); f = ts::sigmoidf_fast(pf); g = ts::tanhf_fast(pg); o = ts::sigmoidf_fast(po);
+  } else {
+    i = ts::sigmoidf_acc(pi); f = ts::sigmoidf_acc(pf); g = tanhf(pg); o = ts::sigmoidf_acc(po);
+  }
+  float c = f * c_prev[idx] + i * g;
+  float h = o * (kFast ? ts::tanhf_fast(c) : tanhf(c));
+  c_out[idx] = c;
+  h_out[idx] = ts::Cvt<T>::from_f(h);
+  T* a = act + (size_t)idx * 4;
+  a[0] = ts::Cvt<T>::from_f(i); a[1] = ts::Cvt<T>::from_f(f);
+  a[2] = ts::Cvt<T>::from_f(g); a[3] = ts::Cvt<T>::from_f(o);
+}
+
+// dh_a / dh_b: the two sources of dL/dh_t (layer above, and the recurrent term); either may be null.
+template <typename T, bool kFast>
+__global__ void lstm_pointwise_bwd_kernel(const T* __restrict__ dh_a, const float* __restrict__ dh_b,
+                                          const float* __restrict__ dc_in, const T* __restrict__ act,
+                                          const float* __restrict__ c_prev, const float* __restrict__ c_new,
+                                          T* __restrict__ dpre, float* __restrict__ dc_out, int B, int H) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * H) return;
+  float dh = 0.f;
+  if (dh_a) dh += ts::Cvt<T>::to_f(dh_a[idx]);
+  if (dh_b) dh += dh_b[idx];
+  const T* a = act + (size_t)idx * 4;
+  float i = ts::Cvt<T>::to_f(a[0]), f = ts::Cvt<T>::to_f(a[1]);
+  float g = ts::Cvt<T>::to_f(a[2]), o = ts::Cvt<T>::to_f(a[3]);
+  float tc = kFast ? ts::tanhf_fast(c_new[idx]) : tanhf(c_new[idx]);
+  float dc = (dc_in ? dc_in[idx] : 0.f) + dh * o * (1.f - tc * tc);
+  float d_o = dh * tc;
+  float d_i = dc * g, d_f = dc * c_prev[idx], d_g = dc * i;
+  dc_out[idx] = dc * f;
+  T* d = dpre + (size_t)idx * 4;
+  d[0] = ts::Cvt<T>::from_f(d_i * i * (1.f - i));
+  d[1] = ts::Cvt<T>::from_f(d_f * f * (1.f - f));
+  d[2] = ts::Cvt<T>::from_f(d_g * (1.f - g * g));
+  d[3] = ts::Cvt<T>::from_f(d_o * o * (1.f - o));
+}
+
+}  // namespace
+
+extern "C" int ts_lstm_pointwise_fwd(const void* pre, const float* bias, const float* c_prev, void* h_out,
+                                     float* c_out, void* act, int B, int H, int is_bf16, cudaStream_t st) {
+  int n = B * H, thr = 256, blk = (n + thr - 1) / thr;
+  if (is_bf16)
+    lstm_pointwise_fwd_kernel<__nv_bfloat16, true><<<blk, thr, 0, st>>>(
+        (const __nv_bfloat16*)pre, bias, c_prev, (__nv_bfloat16*)h_out, c_out, (__nv_bfloat16*)act, B, H);
+  else
+    lstm_pointwise_fwd_kernel<float, false><<<blk, thr, 0, st>>>((const float*)pre, bias, c_prev, (float*)h_out,
+                                                                 c_out, (float*)act, B, H);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ts_lstm_pointwise_bwd(const void* dh_a, const float* dh_b, const float* dc_in, const void* act,
+                                     const float* c_prev, const float* c_new, void* dpre, float* dc_out, int B,
+                                     int H, int is_bf16, cudaStream_t st) {
+  int n = B * H, thr = 256, blk = (n + thr - 1) / thr;
+  if (is_bf16)
+    lstm_pointwise_bwd_kernel<__nv_bfloat16, true><<<blk, thr, 0, st>>>(
+        (const __nv_bfloat16*)dh_a, dh_b, dc_in, (const __nv_bfloat16*)act, c_prev, c_new, (__nv_bfloat16*)dpre,
+        dc_out, B, H);
+  else
+    lstm_pointwise_bwd_kernel<float, false><<<blk, thr, 0, st>>>((const float*)dh_a, dh_b, dc_in, (const float*)act,
+                                                                  c_prev, c_new, (float*)dpre, dc_out, B, H);
+  return (int)cudaGetLastError();
+}

@@ -1,0 +1,115 @@
+"""TrainEngine: the public "one training step" API (model + flat buffers + optimizer + cross-replica sync).
+
+This is what ``bench.py``, ``__graft_entry__.smoke`` and the per-replica trainer call:
+
+    eng = TrainEngine(cfg, rank, world_size, comm, batch_size=B)
+    loss = eng.step(x, y)            # forward, backward, (fused allreduce +) optimizer update
+
+One step replaces the reference's ``sess.run([train_op, loss], feed_dict=...)`` (/root/reference/src/rnn.py:264-267):
+H2D feed, forward, backward, 14·L+2 ApplyAdam launches, D2H loss.  With ``cuda_graph=True`` the whole step is
+captured once and replayed (launch-bound inner loops belong in CUDA graphs, not in a tracing compiler).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .config import Config
+from .models.classifier import SequenceClassifier
+from .models.recurrent.lstm import clear_weight_decay_collection
+from .ops import functional as F
+from .ops.optim import FlatOptimizer
+from .parallel.comm import Communicator
+
+
+class TrainEngine:
+    def __init__(self, cfg: Config, rank: int = 0, world_size: int = 1, comm: Optional[Communicator] = None,
+                 batch_size: Optional[int] = None, device: Optional[torch.device] = None,
+                 dtype: Optional[torch.dtype] = None, train_optimizer=None):
+        self.cfg = cfg
+        self.rank, self.world_size = rank, world_size
+        self.comm = comm or Communicator(0, 1)
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if (cfg.device != "cpu" and torch.cuda.is_available()) \
+                else torch.device("cpu")
+        self.device = device
+        if dtype is None:
+            dtype = torch.bfloat16 if (device.type == "cuda" and cfg.dtype in ("auto", "bf16", "bfloat16")) else torch.float32
+        self.dtype = dtype
+        F.set_backend(cfg.backend)
+        clear_weight_decay_collection()
+        seed = cfg.seed + (1000003 * (rank + 1) if cfg.independent_init else 0)
+        gen = torch.Generator(device="cpu")
+        gen.manual_seed(seed)
+        self.model = SequenceClassifier(cfg, batch_size=batch_size, device="cpu", generator=gen)
+        self.model.to(device)
+        self.flat = self.model.build_flat()
+        self.comm.adopt(self.flat)
+        self.model.set_compute_dtype(dtype)
+        if train_optimizer is not None:
+            self.optimizer = train_optimizer(cfg.learning_rate)(self.flat)
+        else:
+            self.optimizer = FlatOptimizer(self.flat, cfg.learning_rate, cfg.optimizer, weight_decay=0.0)
+        self.sync_grads = cfg.sync_mode == "grad_allreduce" and world_size > 1
+        self._graph = None
+        self._static = None
+        self.steps_done = 0
+
+    # ---------------------------------------------------------------------------------------------------
+    def _step_eager(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        self.flat.zero_grad()
+        loss, _logits, _correct = self.model(x, y)
+        if self.cfg.weight_decay:
+            from .models.recurrent.lstm import weight_decay_terms
+            loss = loss + torch.stack(weight_decay_terms()).sum()
+        loss.backward()
+        if self.sync_grads:
+            self.comm.grad_step_(self.flat, self.optimizer)
+        else:
+            self.optimizer.step()
+        return loss.detach()
+
+    def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """One full training step on this replica; returns the (detached, device) loss."""
+        self.steps_done += 1
+        if self._graph is None:
+            return self._step_eager(x, y)
+        sx, sy, sloss = self._static
+        sx.copy_(x, non_blocking=True)
+        sy.copy_(y, non_blocking=True)
+        self._graph.replay()
+        return sloss
+
+    def maybe_average(self, force: bool = False):
+        """Parameter-average sync point (reference semantics: once, at the end; or every ``sync_every`` steps)."""
+        cfg = self.cfg
+        if self.world_size <= 1 or cfg.sync_mode != "param_avg":
+            return
+        if force or (cfg.sync_every and self.steps_done % cfg.sync_every == 0):
+            self.comm.average_params_(self.flat, cfg.average_scope)
+
+    # ---------------------------------------------------------------------------------------------------
+    def capture(self, x: torch.Tensor, y: torch.Tensor, warmup: int = 3):
+        """Capture fwd+bwd+update into one CUDA graph (static shapes).  Adam's bias-corrected lr is a host scalar
+        baked at capture time, so graphs are only used with SGD or after the correction has saturated."""
+        assert self.device.type == "cuda"
+        sx, sy = x.clone(), y.clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._step_eager(sx, sy)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            sloss = self._step_eager(sx, sy)
+        self._graph, self._static = g, (sx, sy, sloss)
+        return g
+
+    @torch.no_grad()
+    def evaluate(self, x: torch.Tensor, y: torch.Tensor):
+        h = self.model.features(x)
+        logits = self.model.head(h)
+        from .ops import reference as ref
+        return ref.softmax_xent(logits, y), ref.accuracy(logits, y)

@@ -1,0 +1,156 @@
+"""CUDA LSTM layer op = autograd.Function around the hand-written kernels.
+
+Fast path (bf16, H % 64 == 0, weight slice fits in SMEM, grid <= #SMs): hoisted input projection on the tcgen05
+GEMM (csrc/gemm_tcgen05.cu) + ONE persistent tcgen05 kernel for the whole recurrence in each direction
+(csrc/lstm_seq_tcgen05.cu).  Generic path (any shape / fp32): library GEMM per step + the fused pointwise cell
+kernels (csrc/lstm_pointwise.cu).  Weight gradients are plain library GEMMs over all T at once
+(``[4H, T·B] x [T·B, D+H]``), fp32 output.  Math parity: /root/reference/src/models/recurrent/lstm.py:88-122.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+
+from .cuda_ext import ext
+
+_SYNC_WS = {}
+_SM_COUNT = {}
+FORCE_GENERIC = os.environ.get("LSTM_TS_FORCE_GENERIC", "0") == "1"
+USE_TC_GEMM = os.environ.get("LSTM_TS_TC_GEMM", "1") == "1"
+STATS = {"fast_fwd": 0, "fast_bwd": 0, "generic_fwd": 0, "generic_bwd": 0, "tc_gemm": 0, "kernels": 0}
+
+
+def _sync_ws(device) -> torch.Tensor:
+    key = (device.type, device.index)
+    if key not in _SYNC_WS:
+        _SYNC_WS[key] = torch.zeros(64, dtype=torch.int32, device=device)
+    return _SYNC_WS[key]
+
+
+def check_kernel_errors(device) -> None:
+    """Raise if a persistent kernel hit its bounded-spin timeout (sticky flag, costs one D2H read)."""
+    ws = _SYNC_WS.get((device.type, device.index))
+    if ws is not None and int(ws[63].item()) != 0:
+        raise RuntimeError("lstm_seq kernel aborted: an in-kernel wait timed out (see csrc/lstm_seq_tcgen05.cu)")
+
+
+def _sms(device) -> int:
+    key = device.index
+    if key not in _SM_COUNT:
+        _SM_COUNT[key] = torch.cuda.get_device_properties(device).multi_processor_count
+    return _SM_COUNT[key]
+
+
+def fast_path_supported(B: int, H: int, dtype: torch.dtype, device) -> bool:
+    if FORCE_GENERIC or dtype != torch.bfloat16 or H % 64 != 0:
+        return False
+    tiles_m = (B + 127) // 128
+    tiles_n = H // 16
+    if tiles_m * tiles_n > _sms(device):
+        return False
+    smem = H * 64 * 2 + 4 * 16384 + 2048          # resident slice + 4 stages (+ barriers)
+    return smem <= 227 * 1024 and tiles_m <= 16
+
+
+def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    if a.dtype == torch.float32:
+        return a @ b
+    try:
+        return torch.mm(a, b, out_dtype=torch.float32)
+    except (TypeError, RuntimeError):
+        return (a @ b).float()
+
+
+def _gemm_tn(a: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """a [M,K] @ w[N,K]^T -> [M,N] in a.dtype; tcgen05 kernel when bf16 and aligned, library GEMM otherwise."""
+    if USE_TC_GEMM and a.dtype == torch.bfloat16 and a.shape[1] % 8 == 0 and w.shape[0] % 8 == 0 and a.shape[0] >= 128:
+        STATS["tc_gemm"] += 1
+        STATS["kernels"] += 1
+        return ext().gemm_bf16_tn(a.contiguous(), w.contiguous(), None, False, 0)
+    return a @ w.t()
+
+
+class _LSTMSeqFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_seq, h0, c0, w_x, w_h, bias):
+        E = ext()
+        T, B, D = x_seq.shape
+        H = w_h.shape[1]
+        cd = x_seq.dtype
+        x2d = x_seq.reshape(T * B, D).contiguous()
+        w_x_c = w_x.detach().to(cd).contiguous()
+        w_h_c = w_h.detach().to(cd).contiguous()
+        bias_f = bias.detach().float().contiguous()
+        gx = _gemm_tn(x2d, w_x_c).view(T, B, 4 * H)
+        fast = fast_path_supported(B, H, cd, x_seq.device)
+        c0f = c0.detach().float().contiguous()
+        h0c = h0.detach().to(cd).contiguous()
+        if fast:
+            h_seq, c_seq, act = E.lstm_seq_fwd(gx, w_h_c, bias_f, h0c, c0f, _sync_ws(x_seq.device), 0)
+            STATS["fast_fwd"] += 1
+            STATS["kernels"] += 1
+        else:
+            h_seq = torch.empty(T + 1, B, H, dtype=cd, device=x_seq.device)
+            c_seq = torch.empty(T + 1, B, H, dtype=torch.float32, device=x_seq.device)
+            act = torch.empty(T, B, 4 * H, dtype=cd, device=x_seq.device)
+            h_seq[0].copy_(h0c)
+            c_seq[0].copy_(c0f)
+            w_h_t = w_h_c.t()
+            for t in range(T):
+                pre = torch.addmm(gx[t], h_seq[t], w_h_t)
+                h, c, a = E.lstm_pointwise_fwd(pre, bias_f, c_seq[t])
+                h_seq[t + 1].copy_(h)
+                c_seq[t + 1].copy_(c)
+                act[t].copy_(a)
+            STATS["generic_fwd"] += 1
+            STATS["kernels"] += T
+        ctx.save_for_backward(x2d, h_seq, c_seq, act, w_x_c, w_h_c)
+        ctx.fast = fast
+        ctx.dims = (T, B, D, H)
+        ctx.in_dtypes = (h0.dtype, c0.dtype)
+        return h_seq[1:], c_seq[T]
+
+    @staticmethod
+    def backward(ctx, dh_seq, dc_T):
+        E = ext()
+        x2d, h_seq, c_seq, act, w_x_c, w_h_c = ctx.saved_tensors
+        T, B, D, H = ctx.dims
+        cd = act.dtype
+        dev = act.device
+        dh_seq = (dh_seq if dh_seq is not None else torch.zeros(T, B, H, dtype=cd, device=dev)).to(cd).contiguous()
+        dcT = (dc_T.float().contiguous() if dc_T is not None else torch.zeros(B, H, dtype=torch.float32, device=dev))
+        dhT = torch.zeros(B, H, dtype=torch.float32, device=dev)
+        if ctx.fast:
+            w_hT = w_h_c.t().contiguous()
+            dpre, dh0, dc0 = E.lstm_seq_bwd(dh_seq, w_hT, act, c_seq, dhT, dcT, _sync_ws(dev), 0)
+            STATS["fast_bwd"] += 1
+            STATS["kernels"] += 1
+        else:
+            dpre = torch.empty_like(act)
+            dh_rec: Optional[torch.Tensor] = None
+            dc = dcT
+            for t in range(T - 1, -1, -1):
+                dp, dc = E.lstm_pointwise_bwd(dh_seq[t], dh_rec, dc, act[t], c_seq[t], c_seq[t + 1])
+                dpre[t].copy_(dp)
+                dh_rec = _mm_f32(dp, w_h_c)
+            dh0, dc0 = dh_rec, dc
+            STATS["generic_bwd"] += 1
+            STATS["kernels"] += T
+        dg2d = dpre.view(T * B, 4 * H)
+        dg_t = dg2d.t()
+        dw_x = _mm_f32(dg_t, x2d)
+        dw_h = _mm_f32(dg_t, h_seq[:T].reshape(T * B, H))
+        db = dg2d.float().sum(0)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = _gemm_tn(dg2d, w_x_c.t().contiguous()).view(T, B, D) if cd == torch.bfloat16 else (dg2d @ w_x_c).view(T, B, D)
+        h0_dt, c0_dt = ctx.in_dtypes
+        return dx, dh0.to(h0_dt), dc0.to(c0_dt), dw_x, dw_h, db
+
+
+def lstm_layer_sequence(x_seq, h0, c0, w_x, w_h, bias):
+    """``x_seq [T,B,D]`` (bf16 or fp32) -> ``(h_seq [T,B,H], h_T, c_T)``."""
+    h_seq, c_T = _LSTMSeqFn.apply(x_seq.contiguous(), h0, c0, w_x, w_h, bias)
+    return h_seq, h_seq[-1], c_T

@@ -1,0 +1,156 @@
+"""``--comm fused``: the product path of the cross-replica sync.
+
+The flat parameter / gradient / bf16-shadow buffers of every rank are carved out of ONE NVLink-symmetric
+allocation (``torch.distributed._symmetric_memory``: cuMem VMM handles exchanged between ranks, plus an NVLS
+multicast alias when the fabric supports it).  The sync itself is a single launch of
+``csrc/fused_allreduce.cu`` per rank: reduction over peer / multicast pointers fused with the update
+(average | SGD | Adam) and the bf16 shadow refresh.  NCCL is used only to bootstrap (store, rendezvous) and for
+python-object broadcasts; no NCCL collective and no separate elementwise kernel runs on the sync path.
+
+Replaces ``reduceByKey(mean_weights)`` + ``collect()`` (/root/reference/src/rnn.py:393-407).
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from ..models.flat import FlatParams
+from ..ops.cuda_ext import ext
+from .comm import TorchDistComm
+
+MODE_AVG, MODE_SGD, MODE_ADAM = 0, 1, 2
+TWO_SHOT_BYTES = int(os.environ.get("LSTM_TS_AR_TWO_SHOT_BYTES", str(256 * 1024)))
+AR_BLOCKS = int(os.environ.get("LSTM_TS_AR_BLOCKS", "64"))
+
+
+def _align(x: int, a: int = 4096) -> int:
+    return (x + a - 1) // a * a
+
+
+class SymmetricArena:
+    """One symmetric allocation, sub-allocated at identical offsets on every rank."""
+
+    def __init__(self, nbytes: int, device: torch.device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group.group_name if hasattr(group, "group_name") else group)
+        self.rank = self.hdl.rank
+        self.world = self.hdl.world_size
+        base = [int(p) for p in self.hdl.buffer_ptrs]
+        delta = self.buf.data_ptr() - base[self.rank]
+        self.base = [b + delta for b in base]
+        mc = 0
+        try:
+            mc = int(self.hdl.multicast_ptr or 0)
+        except Exception:                                   # noqa: BLE001
+            mc = 0
+        self.mc_base = (mc + delta) if mc else 0
+        self.off = 0
+        self.nbytes = nbytes
+
+    def carve(self, numel: int, dtype: torch.dtype):
+        nbytes = numel * torch.empty((), dtype=dtype).element_size()
+        off = self.off
+        assert off + nbytes <= self.nbytes, "symmetric arena exhausted"
+        self.off = _align(off + nbytes)
+        t = self.buf[off:off + nbytes].view(dtype)
+        return t, off
+
+    def peers(self, off: int):
+        return [b + off for b in self.base]
+
+    def mc(self, off: int) -> int:
+        return self.mc_base + off if self.mc_base else 0
+
+
+class FusedComm(TorchDistComm):
+    name = "fused"
+
+    def __init__(self, rank: int, world_size: int, device: torch.device, timeout_s: float = 600.0):
+        super().__init__(rank, world_size, "nccl", device, timeout_s)
+        self.name = "fused"
+        self.timeout_s = timeout_s
+        self.arena: Optional[SymmetricArena] = None
+        self.use_multicast = os.environ.get("LSTM_TS_AR_MULTICAST", "auto")
+        self.launches = 0
+
+    # ------------------------------------------------------------------------------------------------
+    def adopt(self, flat: FlatParams):
+        E = ext()
+        n = flat.padded_numel
+        flag_words = E.ar_flag_words()
+        total = 3 * _align(4 * n) + _align(2 * n) + _align(4 * flag_words) + 4096
+        self.arena = SymmetricArena(total, self.device, dist.group.WORLD)
+        A = self.arena
+        self.data, self.off_data = A.carve(n, torch.float32)
+        self.grad, self.off_grad = A.carve(n, torch.float32)
+        self.stage, self.off_stage = A.carve(n, torch.float32)
+        self.shadow, self.off_shadow = A.carve(n, torch.bfloat16)
+        self.flags, self.off_flags = A.carve(flag_words, torch.int32)
+        flat.rebase(self.data, self.grad)
+        had_shadow = flat.shadow is not None
+        flat.shadow = self.shadow
+        flat.refresh_shadow()
+        self.epochs = torch.zeros(E.ar_max_blocks(), dtype=torch.int32, device=self.device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.flat = flat
+        torch.cuda.synchronize(self.device)
+        dist.barrier(device_ids=[self.device.index])
+        return flat
+
+    def _ptr_table(self, off_in: int) -> torch.Tensor:
+        A = self.arena
+        rows = [A.peers(off_in), A.peers(self.off_data), A.peers(self.off_shadow), A.peers(self.off_flags)]
+        return torch.tensor(rows, dtype=torch.int64)
+
+    def _multicast_on(self) -> bool:
+        if self.use_multicast in ("0", "off", "false"):
+            return False
+        return bool(self.arena.mc_base)
+
+    def _launch(self, mode: int, off_in: int, n: int, lr: float = 0.0, b1: float = 0.0, b2: float = 0.0, eps: float = 0.0,
+                wd: float = 0.0, m=None, v=None, force: Optional[str] = None):
+        E = ext()
+        A = self.arena
+        two_shot = (4 * n >= TWO_SHOT_BYTES) if force is None else (force == "two_shot")
+        mc = self._multicast_on() and two_shot
+        if mode == MODE_AVG and not two_shot:
+            off_in_eff = self.off_stage        # one-shot average stages w first
+        else:
+            off_in_eff = off_in
+        ptrs = self._ptr_table(off_in_eff)
+        E.fused_allreduce(ptrs, A.mc(off_in_eff) if mc else 0, A.mc(self.off_data) if mc else 0,
+                          A.mc(self.off_shadow) if mc else 0, m, v, self.epochs, self.err, n, self.rank, self.world_size,
+                          mode, two_shot, mc, AR_BLOCKS, lr, b1, b2, eps, wd, float(self.timeout_s))
+        self.launches += 1
+
+    # ------------------------------------------------------------------------------------------------
+    def average_params_(self, flat: FlatParams, scope: str = "lstm", force: Optional[str] = None):
+        lo, hi = flat.segment(scope)
+        assert lo == 0
+        self._launch(MODE_AVG, self.off_data, hi, force=force)
+
+    def grad_step_(self, flat: FlatParams, optimizer, force: Optional[str] = None):
+        optimizer.step_count += 1
+        n = flat.padded_numel
+        if optimizer.kind == "adam":
+            self._launch(MODE_ADAM, self.off_grad, n, optimizer.bias_corrected_lr(), optimizer.beta1, optimizer.beta2,
+                         optimizer.eps, optimizer.weight_decay, optimizer.m, optimizer.v, force=force)
+        else:
+            self._launch(MODE_SGD, self.off_grad, n, optimizer.lr, wd=optimizer.weight_decay, force=force)
+
+    def check_errors(self):
+        if int(self.err.item()) != 0:
+            raise RuntimeError("fused allreduce: cross-GPU barrier timed out (a peer rank is dead or stalled)")
+
+    def close(self):
+        try:
+            if self.arena is not None:
+                torch.cuda.synchronize(self.device)
+                self.check_errors()
+        finally:
+            super().close()
