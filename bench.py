@@ -55,9 +55,10 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.rows = []
+        self.rows = []          # (arrival time, csv line)
         self.proc = None
         self.gpu = gpu_index
+        self.t_mark = None
 
     def start(self):
         try:
@@ -71,7 +72,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def mark(self):
+        """Start of the timed region: samples before this are warm-up."""
+        self.t_mark = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -83,7 +88,12 @@ class ClockSampler:
             pass
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        timed = [r for (t, r) in self.rows if self.t_mark is None or t >= self.t_mark]
+        window = "timed region"
+        if len(timed) < 2:                       # run shorter than the sampling period: use the samples under load
+            timed = [r for (_, r) in self.rows[1:]] or [r for (_, r) in self.rows]
+            window = "warm-up + timed region"
+        for r in timed:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 8:
                 continue
@@ -95,7 +105,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def dist_env():
@@ -117,10 +127,12 @@ def run_reference(args):
     return 0
 
 
-def timed_loop(torch, dist, world, device, step_fn, steps, warmup):
+def timed_loop(torch, dist, world, device, step_fn, steps, warmup, clocks=None):
     for _ in range(warmup):
         step_fn()
     torch.cuda.synchronize(device)
+    if clocks is not None:
+        clocks.mark()
     if world > 1:
         dist.barrier(device_ids=[device.index])
     torch.cuda.synchronize(device)
@@ -216,7 +228,8 @@ def main():
         par = f"dp{n_gpus}" + ("" if world == 1 else f"-{comm.name}")
 
     clocks.start()
-    ms = timed_loop(torch, dist, world, device, step_dev, args.steps, args.warmup)
+    time.sleep(0.3)
+    ms = timed_loop(torch, dist, world, device, step_dev, args.steps, args.warmup, clocks)
     clk = clocks.stop()
     e2e = None
     if not args.no_e2e:

@@ -178,7 +178,7 @@ Tensor gemm_bf16_tn(const Tensor& A, const Tensor& B, const std::optional<Tensor
 // gx [T,B,4H] bf16 (x·Wx^T, no bias), w_h [4H,H] bf16, bias fp32 [4H], h0 bf16 [B,H], c0 fp32 [B,H]
 // -> h_seq [T+1,B,H] bf16 (row 0 = h0), c_seq [T+1,B,H] fp32, act [T,B,4H] bf16
 std::vector<Tensor> lstm_seq_fwd(const Tensor& gx, const Tensor& w_h, const Tensor& bias, const Tensor& h0,
-                                 const Tensor& c0, Tensor sync_ws, int64_t variant) {
+                                 const Tensor& c0, Tensor sync_ws, int64_t variant, std::optional<Tensor> dbg) {
   chk_cuda(gx, "gx"); chk_cuda(w_h, "w_h"); chk_cuda(bias, "bias"); chk_cuda(h0, "h0"); chk_cuda(c0, "c0");
   c10::cuda::CUDAGuard gd(gx.device());
   int T = gx.size(0), B = gx.size(1), H = gx.size(2) / 4;
@@ -189,8 +189,8 @@ std::vector<Tensor> lstm_seq_fwd(const Tensor& gx, const Tensor& w_h, const Tens
   c_seq[0].copy_(c0);
   sync_ws.narrow(0, 0, 16).zero_();       // step counters restart at 0 every launch; [63] = sticky error flag
   check(ts_lstm_seq_fwd(gx.data_ptr(), w_h.data_ptr(), bias.data_ptr<float>(), h_seq.data_ptr(), c_seq.data_ptr<float>(),
-                        act.data_ptr(), nullptr, nullptr, nullptr, T, B, H, (unsigned int*)sync_ws.data_ptr<int>(),
-                        (int)variant, stream()), "lstm_seq_fwd");
+                        act.data_ptr(), nullptr, dbg.has_value() ? dbg->data_ptr() : nullptr, nullptr, T, B, H,
+                        (unsigned int*)sync_ws.data_ptr<int>(), (int)variant, stream()), "lstm_seq_fwd");
   return {h_seq, c_seq, act};
 }
 
@@ -198,7 +198,8 @@ std::vector<Tensor> lstm_seq_fwd(const Tensor& gx, const Tensor& w_h, const Tens
 // act/c_seq from forward, dhT fp32 [B,H] / dcT fp32 [B,H] extra grads into the final state (may be zeros)
 // -> dpre [T,B,4H] bf16, dh0 fp32 [B,H], dc0 fp32 [B,H]
 std::vector<Tensor> lstm_seq_bwd(const Tensor& dh_seq, const Tensor& w_hT, const Tensor& act, const Tensor& c_seq,
-                                 const Tensor& dhT, const Tensor& dcT, Tensor sync_ws, int64_t variant) {
+                                 const Tensor& dhT, const Tensor& dcT, Tensor sync_ws, int64_t variant,
+                                 std::optional<Tensor> dbg) {
   chk_cuda(dh_seq, "dh_seq"); chk_cuda(w_hT, "w_hT"); chk_cuda(act, "act"); chk_cuda(c_seq, "c_seq");
   c10::cuda::CUDAGuard gd(act.device());
   int T = act.size(0), B = act.size(1), H = act.size(2) / 4;
@@ -207,7 +208,7 @@ std::vector<Tensor> lstm_seq_bwd(const Tensor& dh_seq, const Tensor& w_hT, const
   auto dc0 = dcT.clone();
   sync_ws.narrow(0, 0, 16).zero_();
   check(ts_lstm_seq_bwd(dh_seq.data_ptr(), w_hT.data_ptr(), act.data_ptr(), c_seq.data_ptr<float>(), dpre.data_ptr(),
-                        dh0.data_ptr<float>(), dc0.data_ptr<float>(), nullptr, nullptr, T, B, H,
+                        dh0.data_ptr<float>(), dc0.data_ptr<float>(), dbg.has_value() ? dbg->data_ptr() : nullptr, nullptr, T, B, H,
                         (unsigned int*)sync_ws.data_ptr<int>(), (int)variant, stream()), "lstm_seq_bwd");
   return {dpre, dh0, dc0};
 }
@@ -227,6 +228,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ar_max_blocks", []() { return ts_ar_max_blocks(); });
   m.def("ar_flag_words", []() { return ts_ar_flag_words(); });
   m.def("gemm_bf16_tn", &gemm_bf16_tn);
-  m.def("lstm_seq_fwd", &lstm_seq_fwd);
-  m.def("lstm_seq_bwd", &lstm_seq_bwd);
+  m.def("lstm_seq_fwd", &lstm_seq_fwd, py::arg("gx"), py::arg("w_h"), py::arg("bias"), py::arg("h0"), py::arg("c0"),
+        py::arg("sync_ws"), py::arg("cluster") = 0, py::arg("dbg") = py::none());
+  m.def("lstm_seq_bwd", &lstm_seq_bwd, py::arg("dh_seq"), py::arg("w_hT"), py::arg("act"), py::arg("c_seq"), py::arg("dhT"),
+        py::arg("dcT"), py::arg("sync_ws"), py::arg("variant") = 0, py::arg("dbg") = py::none());
 }

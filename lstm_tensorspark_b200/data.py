@@ -210,8 +210,9 @@ class DeviceShard:
 
 
 class PinnedHostLoader:
-    """Host-resident shard with double-buffered pinned staging: each ``next()`` issues the H2D copy
-    of one batch on a side stream and hands back device tensors (the end-to-end path of bench.py)."""
+    """Host-resident shard in PINNED memory: each ``next()`` issues the host->device copy of one contiguous batch
+    (async, double-buffered device staging) and hands back device tensors — the end-to-end path of bench.py.
+    Shuffling permutes the pinned copy once per pass (not per step), so a step is exactly one H2D DMA per tensor."""
 
     def __init__(self, x: np.ndarray, y: np.ndarray, batch_size: int, device, dtype=torch.float32,
                  shuffle: bool = True, seed: int = 0):
@@ -220,33 +221,37 @@ class PinnedHostLoader:
         self.n = x.shape[0]
         self.batch_size = resolve_batch_size(batch_size, self.n)
         self.per_epoch = self.n // self.batch_size
-        self.rng = np.random.default_rng(seed)
+        self.gen = torch.Generator(device="cpu")
+        self.gen.manual_seed(seed)
         self.shuffle = shuffle
-        self.x_host = torch.as_tensor(x).to(dtype)
-        self.y_host = torch.as_tensor(y)
         cuda = self.device.type == "cuda"
+        self.x_host = torch.as_tensor(x).to(dtype).contiguous()
+        self.y_host = torch.as_tensor(y).contiguous()
+        if cuda:
+            self.x_host = self.x_host.pin_memory()
+            self.y_host = self.y_host.pin_memory()
         shape_x = (self.batch_size,) + tuple(self.x_host.shape[1:])
-        self.stage = [(torch.empty(shape_x, dtype=dtype, pin_memory=cuda),
-                       torch.empty((self.batch_size,), dtype=torch.int64, pin_memory=cuda)) for _ in range(2)]
         self.dev = [(torch.empty(shape_x, dtype=dtype, device=self.device),
                      torch.empty((self.batch_size,), dtype=torch.int64, device=self.device)) for _ in range(2)]
         self._slot = 0
-        self._perm = None
-        self._i = 0
-        self.bytes_per_batch = self.stage[0][0].numel() * self.stage[0][0].element_size() + self.batch_size * 8
+        self._i = self.per_epoch if shuffle else 0
+        self.bytes_per_batch = self.dev[0][0].numel() * self.dev[0][0].element_size() + self.batch_size * 8
+
+    def _reshuffle(self):
+        perm = torch.randperm(self.n, generator=self.gen)
+        xs, ys = self.x_host[perm], self.y_host[perm]
+        self.x_host.copy_(xs)
+        self.y_host.copy_(ys)
 
     def next(self) -> Tuple[torch.Tensor, torch.Tensor]:
-        if self._perm is None or self._i >= self.per_epoch:
-            self._perm = self.rng.permutation(self.n) if self.shuffle else np.arange(self.n)
+        if self._i >= self.per_epoch:
+            if self.shuffle:
+                self._reshuffle()
             self._i = 0
         lo = self._i * self.batch_size
-        idx = torch.from_numpy(self._perm[lo:lo + self.batch_size])
         self._i += 1
-        sx, sy = self.stage[self._slot]
         dx, dy = self.dev[self._slot]
-        torch.index_select(self.x_host, 0, idx, out=sx)
-        torch.index_select(self.y_host, 0, idx, out=sy)
-        dx.copy_(sx, non_blocking=True)
-        dy.copy_(sy, non_blocking=True)
+        dx.copy_(self.x_host[lo:lo + self.batch_size], non_blocking=True)
+        dy.copy_(self.y_host[lo:lo + self.batch_size], non_blocking=True)
         self._slot ^= 1
         return dx, dy

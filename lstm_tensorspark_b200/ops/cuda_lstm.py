@@ -18,6 +18,7 @@ from .cuda_ext import ext
 _SYNC_WS = {}
 _SM_COUNT = {}
 FORCE_GENERIC = os.environ.get("LSTM_TS_FORCE_GENERIC", "0") == "1"
+FWD_CLUSTER = int(os.environ.get("LSTM_TS_FWD_CLUSTER", "0"))     # 0 = auto (largest co-resident multicast cluster)
 USE_TC_GEMM = os.environ.get("LSTM_TS_TC_GEMM", "1") == "1"
 STATS = {"fast_fwd": 0, "fast_bwd": 0, "generic_fwd": 0, "generic_bwd": 0, "tc_gemm": 0, "kernels": 0}
 
@@ -50,7 +51,7 @@ def fast_path_supported(B: int, H: int, dtype: torch.dtype, device) -> bool:
     tiles_n = H // 16
     if tiles_m * tiles_n > _sms(device):
         return False
-    smem = H * 64 * 2 + 4 * 16384 + 2048          # resident slice + 4 stages (+ barriers)
+    smem = H * 64 * 2 + 4 * 16384 + 24576 + 2048   # resident slice + 4 stages + DSMEM exchange (+ barriers)
     return smem <= 227 * 1024 and tiles_m <= 16
 
 
@@ -88,7 +89,7 @@ class _LSTMSeqFn(torch.autograd.Function):
         c0f = c0.detach().float().contiguous()
         h0c = h0.detach().to(cd).contiguous()
         if fast:
-            h_seq, c_seq, act = E.lstm_seq_fwd(gx, w_h_c, bias_f, h0c, c0f, _sync_ws(x_seq.device), 0)
+            h_seq, c_seq, act = E.lstm_seq_fwd(gx, w_h_c, bias_f, h0c, c0f, _sync_ws(x_seq.device), FWD_CLUSTER)
             STATS["fast_fwd"] += 1
             STATS["kernels"] += 1
         else:
@@ -142,7 +143,7 @@ class _LSTMSeqFn(torch.autograd.Function):
         dg_t = dg2d.t()
         dw_x = _mm_f32(dg_t, x2d)
         dw_h = _mm_f32(dg_t, h_seq[:T].reshape(T * B, H))
-        db = dg2d.float().sum(0)
+        db = torch.sum(dg2d, dim=0, dtype=torch.float32)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = _gemm_tn(dg2d, w_x_c.t().contiguous()).view(T, B, D) if cd == torch.bfloat16 else (dg2d @ w_x_c).view(T, B, D)

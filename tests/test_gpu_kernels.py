@@ -1,0 +1,155 @@
+"""Kernel tests (GPU, `pytest -m gpu`): every hand-written sm_100a kernel vs. the plain PyTorch fp32 reference of
+the same op (ops/reference.py).  These run the CUDA path only — a missing extension is an error, not a skip."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def E():
+    from lstm_tensorspark_b200.ops.cuda_ext import ext
+    return ext()
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda", 0)
+
+
+def _ref():
+    from lstm_tensorspark_b200.ops import reference
+    return reference
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+def test_pointwise_cell_fwd_bwd(E, dev, dtype, tol):
+    ref = _ref()
+    torch.manual_seed(0)
+    B, H = 37, 24
+    pre = torch.randn(B, 4 * H, device=dev).to(dtype)
+    bias = torch.randn(4 * H, device=dev)
+    c = torch.randn(B, H, device=dev)
+    h, cn, act = E.lstm_pointwise_fwd(pre, bias, c)
+    pr = (pre.float() + bias).requires_grad_(True)
+    cr = c.clone().requires_grad_(True)
+    i, f, g, o = ref.lstm_gates(pr)
+    c_ref = f * cr + i * g
+    h_ref = o * torch.tanh(c_ref)
+    assert (h.float() - h_ref).abs().max() < tol and (cn - c_ref).abs().max() < tol
+    dh = torch.randn(B, H, device=dev)
+    dc = torch.randn(B, H, device=dev)
+    (h_ref * dh + c_ref * dc).sum().backward()
+    dpre, dcp = E.lstm_pointwise_bwd(dh.to(dtype), None, dc, act, c, cn)
+    assert (dpre.float() - pr.grad).abs().max() < 10 * tol and (dcp - cr.grad).abs().max() < 10 * tol
+
+
+def test_head_xent(E, dev):
+    ref = _ref()
+    torch.manual_seed(0)
+    B, H, C = 50, 96, 7
+    h = torch.randn(B, H, device=dev)
+    W = torch.randn(H, C, device=dev) * 0.1
+    b = torch.randn(C, device=dev)
+    y = torch.randint(0, C, (B,), device=dev)
+    logits, dlog, loss, corr = E.head_xent(h, W, b, y)
+    lr = (h @ W + b).requires_grad_(True)
+    lossr = ref.softmax_xent(lr, y)
+    lossr.backward()
+    assert (logits - lr).abs().max() < 1e-4
+    assert abs(float(loss) / B - float(lossr)) < 1e-5
+    assert (dlog - lr.grad).abs().max() < 1e-6
+    assert int(corr) == int((lr.argmax(1) == y).sum())
+
+
+def test_flat_adam_and_sgd(E, dev):
+    ref = _ref()
+    torch.manual_seed(0)
+    n = 16384
+    p = torch.randn(n, device=dev); g = torch.randn(n, device=dev)
+    m = torch.zeros(n, device=dev); v = torch.zeros(n, device=dev)
+    p2, m2, v2 = p.clone(), m.clone(), v.clone()
+    sh = torch.empty(n, dtype=torch.bfloat16, device=dev)
+    for step in (1, 2, 3):
+        lr_t = 1e-3 * (1 - 0.999 ** step) ** 0.5 / (1 - 0.9 ** step)
+        E.flat_adam(p, g, m, v, sh, lr_t, 0.9, 0.999, 1e-8, 0.0, 0.5)
+        ref.adam_step_(p2, g, m2, v2, step, 1e-3, grad_scale=0.5)
+    assert (p - p2).abs().max() < 1e-5 and (sh.float() - p).abs().max() < 2e-2
+    q = p.clone()
+    E.flat_sgd(p, g, None, 0.1, 0.0, 1.0)
+    assert torch.allclose(p, q - 0.1 * g, atol=1e-6)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 512), (1000, 520, 264), (4096, 4096, 1024)])
+def test_tcgen05_gemm(E, dev, variant, M, N, K):
+    torch.manual_seed(0)
+    A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+    Bm = (torch.randn(N, K, device=dev) * 0.5).bfloat16()
+    bias = torch.randn(N, device=dev)
+    C = E.gemm_bf16_tn(A, Bm, bias, True, variant)
+    R = A.float() @ Bm.float().t() + bias
+    assert (C - R).abs().max() / R.abs().max() < 2e-3
+    Cb = E.gemm_bf16_tn(A, Bm, None, False, variant)
+    assert (Cb.float() - (R - bias)).abs().max() / R.abs().max() < 2e-2
+
+
+def _seq_case(dev, T, B, H, D, tol):
+    from lstm_tensorspark_b200.ops import cuda_lstm
+    ref = _ref()
+    torch.manual_seed(1)
+    params = [torch.randn(T, B, D, device=dev) * 0.5, torch.randn(B, H, device=dev) * 0.1, torch.randn(B, H, device=dev) * 0.1,
+              torch.randn(4 * H, D, device=dev) / D ** 0.5, torch.randn(4 * H, H, device=dev) / H ** 0.5,
+              torch.randn(4 * H, device=dev) * 0.1]
+    pr = [p.bfloat16().float().requires_grad_(True) if i != 2 else p.clone().requires_grad_(True) for i, p in enumerate(params)]
+    hs_r, _, cT_r = ref.lstm_layer_sequence(*pr)
+    wgt = torch.randn_like(hs_r)
+    (hs_r * wgt).sum().backward()
+    pc = [p.clone().requires_grad_(True) for p in params]
+    hs, hT, cT = cuda_lstm.lstm_layer_sequence(pc[0].bfloat16(), pc[1], pc[2], pc[3], pc[4], pc[5])
+    (hs.float() * wgt).sum().backward()
+    torch.cuda.synchronize()
+    cuda_lstm.check_kernel_errors(dev)
+    assert (hs.float() - hs_r).abs().max() < tol
+    assert (cT - cT_r).abs().max() < tol
+    for a, b in zip(pc, pr):
+        rel = (a.grad.float() - b.grad).abs().max() / (b.grad.abs().max() + 1e-12)
+        assert rel < 5 * tol, float(rel)
+
+
+@pytest.mark.parametrize("T,B,H,D", [(3, 128, 64, 64), (5, 100, 128, 72), (4, 256, 256, 128), (8, 256, 1024, 1024)])
+def test_persistent_tcgen05_lstm_sequence(dev, T, B, H, D):
+    from lstm_tensorspark_b200.ops import cuda_lstm
+    n0 = cuda_lstm.STATS["fast_fwd"], cuda_lstm.STATS["fast_bwd"]
+    _seq_case(dev, T, B, H, D, tol=3e-2)
+    assert cuda_lstm.STATS["fast_fwd"] == n0[0] + 1 and cuda_lstm.STATS["fast_bwd"] == n0[1] + 1   # the tcgen05 path ran
+
+
+@pytest.mark.parametrize("T,B,H,D", [(1, 10, 16, 4), (6, 33, 48, 20)])
+def test_generic_shape_lstm_sequence(dev, T, B, H, D):
+    from lstm_tensorspark_b200.ops import cuda_lstm
+    n0 = cuda_lstm.STATS["generic_fwd"]
+    _seq_case(dev, T, B, H, D, tol=3e-2)
+    assert cuda_lstm.STATS["generic_fwd"] == n0 + 1
+
+
+def test_engine_step_trains_and_uses_kernels(dev):
+    import __graft_entry__ as g
+    g.smoke()
+
+
+def test_fp32_iris_shape_on_gpu(dev):
+    """Reference-shaped model (T=1, learned initial state, fp32) on the GPU path vs the CPU reference path."""
+    from lstm_tensorspark_b200.config import Config
+    from lstm_tensorspark_b200.models import SequenceClassifier
+    from lstm_tensorspark_b200.ops import functional as F
+    cfg = Config(hidden_units="16", in_features=4, batch_size=10)
+    g = torch.Generator().manual_seed(0)
+    m_cpu = SequenceClassifier(cfg, batch_size=10, generator=g); m_cpu.build_flat()
+    g = torch.Generator().manual_seed(0)
+    m_gpu = SequenceClassifier(cfg, batch_size=10, generator=g); m_gpu.to(dev); m_gpu.build_flat()
+    x = torch.randn(10, 4); y = torch.randint(0, 3, (10,))
+    l_cpu, _, _ = m_cpu(x, y); l_cpu.backward()
+    l_gpu, _, _ = m_gpu(x.to(dev), y.to(dev)); l_gpu.backward()
+    assert abs(float(l_cpu) - float(l_gpu)) < 1e-4
+    assert (m_cpu.flat.grad - m_gpu.flat.grad.cpu()).abs().max() < 1e-4
