@@ -175,51 +175,50 @@ def check_seq_big():
 
 
 def check_seq_tune():
-    """Forward multicast-cluster sweep + per-phase timestamps of CTA 0 (wait-done / accumulator-ready / signalled)."""
+    """Per-phase timestamps of CTA 0 (wait-done / accumulator-ready / signalled) + per-k-block TMA issue -> landed times."""
     import torch
     from lstm_tensorspark_b200.ops import cuda_lstm
     from lstm_tensorspark_b200.ops.cuda_ext import ext
     E = ext()
     dev = torch.device("cuda")
-    T, B, H, D = 128, 256, 1024, 1024
-    torch.manual_seed(0)
-    gx = (torch.randn(T, B, 4 * H, device=dev) * 0.5).bfloat16()
-    whb = (torch.randn(4 * H, H, device=dev) / H ** 0.5).bfloat16()
-    bias = torch.zeros(4 * H, device=dev)
-    h0 = torch.zeros(B, H, device=dev).bfloat16(); c0 = torch.zeros(B, H, device=dev)
-    ws = cuda_lstm._sync_ws(dev)
-    ref_h = None
-    for c in (1, 2, 4, 8):
-        try:
-            hs, cs, act = E.lstm_seq_fwd(gx, whb, bias, h0, c0, ws, c)
-            torch.cuda.synchronize()
-            cuda_lstm.check_kernel_errors(dev)
-            if ref_h is None:
-                ref_h = hs
-            ms = _time_ms(lambda: E.lstm_seq_fwd(gx, whb, bias, h0, c0, ws, c), iters=5, warm=2)
-            dbg = torch.zeros(4 * (T + 2), dtype=torch.int64, device=dev)
-            E.lstm_seq_fwd(gx, whb, bias, h0, c0, ws, c, dbg)
-            torch.cuda.synchronize()
-            d = dbg.view(-1, 4)[8:24].cpu()
-            waited, accum, sig = d[:, 0], d[:, 1], d[:, 2]
-            _emit("fwd_cluster", cluster=c, ms=ms, us_per_step=ms * 1e3 / T, same=bool(torch.equal(hs, ref_h)),
-                  load_mma_us=float((accum - waited).float().mean()) / 1e3, epi_us=float((sig - accum).float().mean()) / 1e3,
-                  sync_us=float((waited[1:] - sig[:-1]).float().mean()) / 1e3)
-        except Exception as e:                     # noqa: BLE001
-            _emit("fwd_cluster", cluster=c, error=repr(e)[:300])
-    hs, cs, act = E.lstm_seq_fwd(gx, whb, bias, h0, c0, ws, 0)
-    whT = whb.t().contiguous()
-    dh = (torch.randn(T, B, H, device=dev) * 0.1).bfloat16()
-    z = torch.zeros(B, H, device=dev)
-    ms = _time_ms(lambda: E.lstm_seq_bwd(dh, whT, act, cs, z, z, ws, 0), iters=5, warm=2)
-    dbg = torch.zeros(4 * (T + 2), dtype=torch.int64, device=dev)
-    E.lstm_seq_bwd(dh, whT, act, cs, z, z, ws, 0, dbg)
-    torch.cuda.synchronize()
-    cuda_lstm.check_kernel_errors(dev)
-    d = dbg.view(-1, 4)[8:24].cpu()
-    waited, accum, sig = d[:, 0], d[:, 1], d[:, 2]
-    _emit("bwd_splitk", ms=ms, us_per_step=ms * 1e3 / T, load_mma_us=float((accum - waited).float().mean()) / 1e3,
-          epi_us=float((sig - accum).float().mean()) / 1e3, sync_us=float((waited[1:] - sig[:-1]).float().mean()) / 1e3)
+    for (T, B, H) in ((32, 256, 1024),):
+        torch.manual_seed(0)
+        gx = (torch.randn(T, B, 4 * H, device=dev) * 0.5).bfloat16()
+        whb = (torch.randn(4 * H, H, device=dev) / H ** 0.5).bfloat16()
+        bias = torch.zeros(4 * H, device=dev)
+        h0 = torch.zeros(B, H, device=dev).bfloat16(); c0 = torch.zeros(B, H, device=dev)
+        ws = cuda_lstm._sync_ws(dev)
+        for (tiles, st, mode) in ((1, 4, 0), (1, 6, 0), (1, 4, 1), (1, 4, 2), (2, 6, 0)):
+            v = tiles + 16 * st + 4096 * mode
+            try:
+                ms = _time_ms(lambda: E.lstm_seq_fwd(gx, whb, bias, h0, c0, ws, v), iters=5, warm=2)
+                dbg = torch.zeros(4 * (T + 2) + 64, dtype=torch.int64, device=dev)
+                E.lstm_seq_fwd(gx, whb, bias, h0, c0, ws, v, dbg)
+                torch.cuda.synchronize()
+                cuda_lstm.check_kernel_errors(dev)
+                d = dbg[:4 * (T + 2)].view(-1, 4)[8:24].cpu()
+                waited, accum, sig = d[:, 0], d[:, 1], d[:, 2]
+                nk = H // 64
+                kb = dbg[4 * (T + 2):].cpu()
+                t0 = int(d[0, 0])
+                issue = [(int(x) - t0) for x in kb[:nk]]
+                landed = [(int(x) - t0) for x in kb[32:32 + nk]]
+                _emit("fwd_variant", T=T, B=B, H=H, tiles=tiles, stages=st, debug_mode=mode, us_per_step=ms * 1e3 / T,
+                      load_mma_us=float((accum - waited).float().mean()) / 1e3, epi_us=float((sig - accum).float().mean()) / 1e3,
+                      sync_us=float((waited[1:] - sig[:-1]).float().mean()) / 1e3, 
+                      accum_ns=int(d[0, 1]) - t0)
+            except Exception as e:                     # noqa: BLE001
+                _emit("fwd_variant", T=T, B=B, H=H, tiles=tiles, stages=st, error=repr(e)[:300])
+
+
+def check_umma():
+    import torch
+    from lstm_tensorspark_b200.ops.cuda_ext import ext
+    E = ext()
+    for mode in (0, 1, 2, 3, 4):
+        for (M, N) in ((128, 64), (128, 128), (128, 256)):
+            out = E.umma_bench(M, N, 4000, mode).cpu()
+            _emit("umma", mode=mode, M=M, N=N, cycles_per_mma=float(out[0]) / float(out[1]), cycles_per_group_of_4=4 * float(out[0]) / float(out[1]))
 
 
 def check_generic():
@@ -245,7 +244,7 @@ def check_iris_gpu():
     _emit("iris_gpu_standalone", rc=r.returncode, tail=(r.stdout + r.stderr)[-600:])
 
 
-CHECKS = {"seq_tune": check_seq_tune, "env": check_env, "simple": check_simple, "gemm": check_gemm, "generic": check_generic, "seq_small": check_seq_small,
+CHECKS = {"umma": check_umma, "seq_tune": check_seq_tune, "env": check_env, "simple": check_simple, "gemm": check_gemm, "generic": check_generic, "seq_small": check_seq_small,
           "seq_big": check_seq_big, "engine": check_engine, "iris_gpu": check_iris_gpu}
 
 

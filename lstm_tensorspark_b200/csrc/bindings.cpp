@@ -34,6 +34,7 @@ int ts_lstm_seq_fwd(const void*, const void*, const float*, const void*, const f
                     int, int, unsigned int*, int, cudaStream_t);
 int ts_lstm_seq_bwd(const void*, const void*, const void*, const float*, const void*, float*, float*, void*, void*, int,
                     int, int, unsigned int*, int, cudaStream_t);
+int ts_umma_bench(int, int, int, int, long long*, cudaStream_t);
 const char* ts_last_error();
 }
 
@@ -188,8 +189,21 @@ std::vector<Tensor> lstm_seq_fwd(const Tensor& gx, const Tensor& w_h, const Tens
   h_seq[0].copy_(h0);
   c_seq[0].copy_(c0);
   sync_ws.narrow(0, 0, 16).zero_();       // step counters restart at 0 every launch; [63] = sticky error flag
+  // streamed-operand images: [T+1][tiles_m][H/64][128][64] bf16, 128B-swizzled; slot 0 = h0
+  const int tiles_m = (B + 127) / 128, nkb = H / 64;
+  auto tiled = torch::empty({(int64_t)(T + 1), tiles_m, nkb, 128, 64}, gx.options());
+  {
+    auto hp = torch::zeros({tiles_m * 128, H}, gx.options());
+    hp.narrow(0, 0, B).copy_(h0);
+    auto v = hp.view({tiles_m, 128, nkb, 8, 8}).permute({0, 2, 1, 3, 4});            // [tm, kb, r, chunk, 8]
+    auto r = torch::arange(128, torch::TensorOptions().device(gx.device()).dtype(torch::kInt64)).remainder(8).view({128, 1});
+    auto c = torch::arange(8, torch::TensorOptions().device(gx.device()).dtype(torch::kInt64)).view({1, 8});
+    auto src = c.bitwise_xor(r);                                                       // position p holds chunk p ^ (r&7)
+    auto idx = src.view({1, 1, 128, 8, 1}).expand({tiles_m, nkb, 128, 8, 8});
+    tiled[0].copy_(v.gather(3, idx).reshape({tiles_m, nkb, 128, 64}));
+  }
   check(ts_lstm_seq_fwd(gx.data_ptr(), w_h.data_ptr(), bias.data_ptr<float>(), h_seq.data_ptr(), c_seq.data_ptr<float>(),
-                        act.data_ptr(), nullptr, dbg.has_value() ? dbg->data_ptr() : nullptr, nullptr, T, B, H,
+                        act.data_ptr(), nullptr, dbg.has_value() ? dbg->data_ptr() : nullptr, tiled.data_ptr(), T, B, H,
                         (unsigned int*)sync_ws.data_ptr<int>(), (int)variant, stream()), "lstm_seq_fwd");
   return {h_seq, c_seq, act};
 }
@@ -207,10 +221,18 @@ std::vector<Tensor> lstm_seq_bwd(const Tensor& dh_seq, const Tensor& w_hT, const
   auto dh0 = dhT.clone();
   auto dc0 = dcT.clone();
   sync_ws.narrow(0, 0, 16).zero_();
+  const int tiles_m = (B + 127) / 128;
+  auto tiled = torch::empty({(int64_t)T, tiles_m, 4 * H / 64, 128, 64}, act.options());   // dG images, written by the kernel
   check(ts_lstm_seq_bwd(dh_seq.data_ptr(), w_hT.data_ptr(), act.data_ptr(), c_seq.data_ptr<float>(), dpre.data_ptr(),
-                        dh0.data_ptr<float>(), dc0.data_ptr<float>(), dbg.has_value() ? dbg->data_ptr() : nullptr, nullptr, T, B, H,
+                        dh0.data_ptr<float>(), dc0.data_ptr<float>(), dbg.has_value() ? dbg->data_ptr() : nullptr, tiled.data_ptr(), T, B, H,
                         (unsigned int*)sync_ws.data_ptr<int>(), (int)variant, stream()), "lstm_seq_bwd");
   return {dpre, dh0, dc0};
+}
+
+Tensor umma_bench(int64_t M, int64_t N, int64_t iters, int64_t mode) {
+  auto out = torch::zeros({2}, torch::TensorOptions().device(torch::kCUDA).dtype(torch::kInt64));
+  check(ts_umma_bench((int)M, (int)N, (int)iters, (int)mode, (long long*)out.data_ptr<int64_t>(), stream()), "umma_bench");
+  return out;
 }
 
 }  // namespace
@@ -228,6 +250,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ar_max_blocks", []() { return ts_ar_max_blocks(); });
   m.def("ar_flag_words", []() { return ts_ar_flag_words(); });
   m.def("gemm_bf16_tn", &gemm_bf16_tn);
+  m.def("umma_bench", &umma_bench);
   m.def("lstm_seq_fwd", &lstm_seq_fwd, py::arg("gx"), py::arg("w_h"), py::arg("bias"), py::arg("h0"), py::arg("c0"),
         py::arg("sync_ws"), py::arg("cluster") = 0, py::arg("dbg") = py::none());
   m.def("lstm_seq_bwd", &lstm_seq_bwd, py::arg("dh_seq"), py::arg("w_hT"), py::arg("act"), py::arg("c_seq"), py::arg("dhT"),

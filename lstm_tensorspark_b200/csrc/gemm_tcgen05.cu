@@ -76,43 +76,53 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * BLOCK_M, n0 = (tile % tiles_n) * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          tc::mbar_wait(&empty[stage], phase ^ 1);
-          tc::mbar_expect_tx(&full[stage], C::kStageBytes);
-          tc::tma_load_2d(smem_a + stage * C::kABytes, &tmap_a, &full[stage], kb * BLOCK_K, m0);
-          tc::tma_load_2d(smem_b + stage * C::kBBytes, &tmap_b, &full[stage], kb * BLOCK_K, n0);
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+    // whole warp in uniform control flow, one elected lane issues (keeps addresses in uniform registers)
+    const uint32_t full0 = tc::smem_u32(full), empty0 = tc::smem_u32(empty);
+    const uint32_t sa0 = tc::smem_u32(smem_a), sb0 = tc::smem_u32(smem_b);
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * BLOCK_M, n0 = (tile % tiles_n) * BLOCK_N;
+      for (int kb = 0, k0 = 0; kb < num_kb; ++kb, k0 += BLOCK_K) {
+        const uint32_t eb = empty0 + 8 * stage, fb = full0 + 8 * stage;
+        while (!tc::mbar_try_wait_u32(eb, phase ^ 1)) {}
+        if (tc::elect_one()) {
+          tc::mbar_expect_tx_u32(fb, C::kStageBytes);
+          tc::tma_load_2d_u32(sa0 + stage * C::kABytes, &tmap_a, fb, k0, m0);
+          tc::tma_load_2d_u32(sb0 + stage * C::kBBytes, &tmap_b, fb, k0, n0);
         }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc_bf16_f32(BLOCK_M, BLOCK_N);
-      int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        tc::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    // whole warp in uniform control flow; one elected lane issues every MMA; descriptors advance by adds
+    constexpr uint32_t idesc = tc::make_idesc_bf16_f32(BLOCK_M, BLOCK_N);
+    const uint32_t full0 = tc::smem_u32(full), empty0 = tc::smem_u32(empty);
+    const uint32_t tfull0 = tc::smem_u32(tmem_full), tempty0 = tc::smem_u32(tmem_empty);
+    const uint64_t da0 = tc::desc_kmajor_sw128(tc::smem_u32(smem_a));
+    const uint64_t db0 = tc::desc_kmajor_sw128(tc::smem_u32(smem_b));
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      while (!tc::mbar_try_wait_u32(tempty0 + 8 * acc, acc_phase ^ 1)) {}
+      tc::fence_after_sync();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        while (!tc::mbar_try_wait_u32(full0 + 8 * stage, phase)) {}
         tc::fence_after_sync();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          tc::mbar_wait(&full[stage], phase);
-          tc::fence_after_sync();
-          const uint64_t da = tc::desc_kmajor_sw128(tc::smem_u32(smem_a + stage * C::kABytes));
-          const uint64_t db = tc::desc_kmajor_sw128(tc::smem_u32(smem_b + stage * C::kBBytes));
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            tc::mma_bf16_ss(d_tmem, tc::desc_advance(da, k * UMMA_K * 2), tc::desc_advance(db, k * UMMA_K * 2), idesc,
-                            (kb | k) != 0);
-          tc::mma_commit(&empty[stage]);                 // smem slot reusable once these MMAs retire
-          if (kb == num_kb - 1) tc::mma_commit(&tmem_full[acc]);
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        if (tc::elect_one()) {
+          const uint64_t da = da0 + (uint64_t)(stage * (C::kABytes >> 4));
+          const uint64_t db = db0 + (uint64_t)(stage * (C::kBBytes >> 4));
+          if (kb == 0) tc::mma_bf16_ss_first(d_tmem, da, db, idesc); else tc::mma_bf16_ss_acc(d_tmem, da, db, idesc);
+          tc::mma_bf16_ss_acc(d_tmem, da + 2, db + 2, idesc);
+          tc::mma_bf16_ss_acc(d_tmem, da + 4, db + 4, idesc);
+          tc::mma_bf16_ss_acc(d_tmem, da + 6, db + 6, idesc);
+          tc::mma_commit_u32(empty0 + 8 * stage);        // smem slot reusable once these MMAs retire
+          if (kb == num_kb - 1) tc::mma_commit_u32(tfull0 + 8 * acc);
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= kEpiWarp0) {
     const int ew = warp - kEpiWarp0;                     // == warp % 4 : TMEM lane quarter this warp may read

@@ -37,20 +37,19 @@ constexpr int BM = 128;           // batch rows per CTA (UMMA M)
 constexpr int BN = 64;            // accumulator columns per CTA (UMMA N)
 constexpr int BK = 64;            // K per pipeline stage (one 128 B swizzle atom of bf16)
 constexpr int UK = 16;            // UMMA K
-constexpr int kStages = 4;
-constexpr int kThreads = 256;
+constexpr int kMaxStages = 8;
 constexpr int kEpiWarp0 = 4;
 constexpr int kABytes = BM * BK * 2;          // 16 KB
 constexpr int kWBlockBytes = BN * BK * 2;     // 8 KB per 64-wide K block
-constexpr int kXchgBytes = 3 * BM * 16 * 4;   // backward: 3 foreign partial chunks [128 x 16] fp32
+constexpr int kXchgBytes = 4 * BM * 16 * 2;   // backward, per batch tile: 4 source slots of [128 x 16] bf16 partial chunks
 constexpr long long kSpinLimit = 6000000000LL;   // ~3 s of SM clocks: a bug surfaces as an error, not a hung GPU
 
 struct SeqSmem {
-  uint64_t full[kStages];
-  uint64_t empty[kStages];
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
   uint64_t w_full;
-  uint64_t tmem_full;
-  uint64_t xchg_full;
+  uint64_t tmem_full[2];
+  uint64_t xchg_full[2];
   uint32_t tmem_slot;
   int abort_flag;
   float bias[64];
@@ -68,6 +67,9 @@ TC_DEVICE uint32_t mapa(uint32_t local_smem_addr, uint32_t cta) {
 }
 TC_DEVICE void st_cluster_f4(uint32_t addr, float4 v) {
   asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+TC_DEVICE void st_cluster_u4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 TC_DEVICE void mbar_arrive_remote(uint32_t remote_bar_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
@@ -132,6 +134,7 @@ TC_DEVICE uint4 ldg_nc16(const void* p) {
 TC_DEVICE void stg16(void* p, uint4 v) {
   asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+TC_DEVICE void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 TC_DEVICE float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
 TC_DEVICE float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 TC_DEVICE uint32_t pack_bf2(float a, float b) {
@@ -151,17 +154,27 @@ struct SeqParams {
   __nv_bfloat16* dpre;         // [T,B,4H]
   float* dh0;                  // [B,H] in: dL/dh_T extra, out: dL/dh_0
   float* dc0;                  // [B,H] in: dL/dc_T, out: dL/dc_0
+  __nv_bfloat16* a_tiled;      // streamed operand as pre-swizzled SMEM images: [time][tiles_m][K/64][128 rows][64] (16 KB blocks)
+  int tiles_m;
+  int debug_mode;              // timing experiments only: 1 = skip operand loads, 2 = skip MMAs (results are garbage)
   unsigned int* sync;          // [tiles_m] step counters; [63] error flag
   unsigned long long* dbg;     // optional [steps][4] timestamps of CTA 0 (ns)
   int T, B, H;
   int tiles_n;                 // CTAs per batch tile
 };
 
-// Forward : CTA (mb, nb)      -> gate columns [64 nb, +64) = hidden [16 nb, +16);   K = H;  cluster = kCluster CTAs along nb (multicast)
-// Backward: CTA (mb, nb2, ks) -> partial dh columns [64 nb2, +64) over gate-column quarter ks (K = H); cluster = 4 (ks);
-//           after the DSMEM reduce-scatter member ks owns hidden [64 nb2 + 16 ks, +16).
-template <bool kBwd, int kCluster>
-__global__ void __launch_bounds__(kThreads, 1)
+// Work decomposition
+//   forward : CTA (g, nb)      -> gate columns [64 nb, +64) = hidden [16 nb, +16), K = H, for the kTiles batch tiles
+//                                 mb = g*kTiles + tile.  With kTiles = 2 a CTA ALTERNATES two independent batch tiles:
+//                                 the epilogue + grid-barrier latency of one tile hides under the operand stream of the
+//                                 other, and the weight slice is shared, so the operand replication (the L2->SM fabric
+//                                 traffic that bounds the step) halves.
+//   backward: CTA (g, nb2, ks) -> partial dh columns [64 nb2, +64) over gate-column quarter ks (K = H); the 4 ks form a
+//                                 cluster; after the DSMEM reduce-scatter member ks owns hidden [64 nb2 + 16 ks, +16).
+// Warps: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, then 4 epilogue warps per batch tile
+// (warp % 4 = TMEM lane quarter; one thread = one batch row, 64 accumulator columns in two passes of 32).
+template <bool kBwd, int kTiles, int kStages>
+__global__ void __launch_bounds__(128 + 128 * kTiles, 1)
 lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                 const SeqParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -169,174 +182,218 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int num_kb = p.H / BK;
   uint8_t* smem_w = smem;                                    // resident weight slice: num_kb blocks of [64 x 64]
   uint8_t* smem_a = smem + (size_t)num_kb * kWBlockBytes;    // kStages x 16 KB
-  uint8_t* smem_x = smem_a + kStages * kABytes;              // backward: DSMEM exchange buffer
-  SeqSmem* ss = reinterpret_cast<SeqSmem*>(smem_x + (kBwd ? kXchgBytes : 0));
+  uint8_t* smem_x = smem_a + kStages * kABytes;              // backward: DSMEM exchange buffers (bf16), one per tile
+  SeqSmem* ss = reinterpret_cast<SeqSmem*>(smem_x + (kBwd ? kTiles * kXchgBytes : 0));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mb = blockIdx.x / p.tiles_n;
-  const int in_mb = blockIdx.x % p.tiles_n;
-  const uint32_t crank = kCluster > 1 ? cluster_ctarank() : 0;
-  // forward: nb = in_mb.  backward: cluster of 4 = the 4 K-quarters of one (mb, nb2)
-  const int nb = kBwd ? in_mb / 4 : in_mb;
+  const int g = blockIdx.x / p.tiles_n;                      // batch-tile group
+  const int in_g = blockIdx.x % p.tiles_n;
+  const uint32_t crank = kBwd ? cluster_ctarank() : 0;
+  const int nb = kBwd ? in_g / 4 : in_g;
   const int ks = kBwd ? (int)crank : 0;
-  unsigned int* counter = p.sync + mb;
   volatile int* abort_flag = &ss->abort_flag;
-  const int steps = kBwd ? p.T + 1 : p.T;       // backward runs one extra GEMM to produce dh_0
-  const bool mcast = !kBwd && kCluster > 1;
-  const uint16_t cmask = (uint16_t)((1u << kCluster) - 1);
+  const int steps = kBwd ? p.T + 1 : p.T;                    // backward runs one extra GEMM to produce dh_0
+  constexpr int kTmemCols = kTiles == 2 ? 128 : 64;
 
   if (threadIdx.x == 0) {
     ss->abort_flag = 0;
     tc::prefetch_tmap(&tmap_a);
     tc::prefetch_tmap(&tmap_w);
-    for (int s = 0; s < kStages; ++s) { tc::mbar_init(&ss->full[s], 1); tc::mbar_init(&ss->empty[s], mcast ? kCluster : 1); }
+    for (int s = 0; s < kStages; ++s) { tc::mbar_init(&ss->full[s], 1); tc::mbar_init(&ss->empty[s], 1); }
     tc::mbar_init(&ss->w_full, 1);
-    tc::mbar_init(&ss->tmem_full, 1);
-    tc::mbar_init(&ss->xchg_full, 3);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&ss->tmem_full[i], 1); tc::mbar_init(&ss->xchg_full[i], 4); }
     tc::fence_barrier_init();
   }
   if (!kBwd && threadIdx.x >= 64 && threadIdx.x < 128) ss->bias[threadIdx.x - 64] = p.bias[nb * BN + threadIdx.x - 64];
-  if (warp == 2) { tc::tmem_alloc(&ss->tmem_slot, 64); tc::tmem_relinquish(); }
+  if (warp == 2) { tc::tmem_alloc(&ss->tmem_slot, kTmemCols); tc::tmem_relinquish(); }
   tc::fence_before_sync();
   __syncthreads();
-  if (kCluster > 1) cluster_sync_all();        // peers' mbarriers are initialised before anyone multicasts / arrives remotely
+  if (kBwd) cluster_sync_all();                 // peers' mbarriers are initialised before anyone arrives remotely
   tc::fence_after_sync();
   const uint32_t tmem_d = ss->tmem_slot;
 
   if (warp == 0) {
     // ======================================================================== TMA producer
-    if (lane == 0) {
-      tc::mbar_expect_tx(&ss->w_full, (uint32_t)(num_kb * kWBlockBytes));
+    // whole warp, uniform control flow; one elected lane issues (see tc::elect_one)
+    const uint32_t w_bar = tc::smem_u32(&ss->w_full);
+    if (tc::elect_one()) {
+      tc::mbar_expect_tx_u32(w_bar, (uint32_t)(num_kb * kWBlockBytes));
       // forward: rows = gate columns [64 nb, +64) of W_h [4H, H].  backward: rows = hidden columns [64 nb, +64) of
       // W_h^T [H, 4H], K offset = quarter ks.
       for (int kb = 0; kb < num_kb; ++kb)
-        tc::tma_load_2d(smem_w + (size_t)kb * kWBlockBytes, &tmap_w, &ss->w_full, (kBwd ? ks * p.H : 0) + kb * BK, nb * BN);
-      int stage = 0; uint32_t phase = 0;
-      bool ok = true;
-      for (int s = kBwd ? 1 : 0; s < steps && ok; ++s) {
-        // forward step s consumes h_seq[s] (rows written by step s-1); backward iteration s consumes dG[T-s]
-        if (s > 0) ok = wait_counter(counter, (unsigned)s * p.tiles_n, abort_flag);
+        tc::tma_load_2d_u32(tc::smem_u32(smem_w) + kb * kWBlockBytes, &tmap_w, w_bar, (kBwd ? ks * p.H : 0) + kb * BK, nb * BN);
+    }
+    __syncwarp();
+    const uint32_t full0 = tc::smem_u32(&ss->full[0]), empty0 = tc::smem_u32(&ss->empty[0]), a0 = tc::smem_u32(smem_a);
+    const int nkb_all = (kBwd ? 4 : 1) * num_kb;
+    uint32_t stage = 0, phase = 0;
+    bool ok = true;
+    for (int s = kBwd ? 1 : 0; s < steps && ok; ++s) {
+      const int tsl = kBwd ? p.T - s : s;       // forward step s consumes h_seq[s]; backward iteration s consumes dG[T-s]
+      for (int tile = 0; tile < kTiles && ok; ++tile) {
+        const int mb = g * kTiles + tile;
+        if (s > 0) ok = wait_counter(p.sync + mb, (unsigned)s * p.tiles_n, abort_flag);
         asm volatile("fence.proxy.async.global;" ::: "memory");
-        if (p.dbg && blockIdx.x == 0) p.dbg[4 * s + 0] = gtime();
-        const int tsl = kBwd ? p.T - s : s;
-        for (int kb = 0; kb < num_kb && ok; ++kb) {
-          ok = wait_bar<false>(&ss->empty[stage], phase ^ 1, abort_flag);
-          if (!ok) break;
-          tc::mbar_expect_tx(&ss->full[stage], kABytes);
-          const int kcol = (kBwd ? ks * p.H : 0) + kb * BK;
-          if (!mcast) {
-            tc::tma_load_3d(smem_a + stage * kABytes, &tmap_a, &ss->full[stage], kcol, mb * BM, tsl);
-          } else if ((kb % kCluster) == (int)crank) {
-            tma_load_3d_mc(smem_a + stage * kABytes, &tmap_a, &ss->full[stage], kcol, mb * BM, tsl, cmask);
+        if (p.dbg && blockIdx.x == 0 && tile == 0 && lane == 0) p.dbg[4 * s + 0] = gtime();
+        // contiguous 16 KB blocks = the 128B-swizzled K-major [128 x 64] tile images written by the epilogues
+        const __nv_bfloat16* src = p.a_tiled + (((size_t)tsl * p.tiles_m + mb) * nkb_all + (kBwd ? ks * num_kb : 0)) * (BM * BK);
+        for (int kb = 0; kb < num_kb; ++kb, src += BM * BK) {
+          if (!tc::mbar_try_wait_u32(empty0 + 8 * stage, phase ^ 1)) {
+            ok = wait_bar<false>(&ss->empty[stage], phase ^ 1, abort_flag);
+            if (!ok) break;
           }
+          if (tc::elect_one()) {
+            const uint32_t fb = full0 + 8 * stage;
+            if (p.debug_mode == 1) {
+              tc::mbar_arrive(&ss->full[stage]);
+            } else {
+              tc::mbar_expect_tx_u32(fb, kABytes);
+              tc::bulk_load_1d_u32(a0 + stage * kABytes, src, kABytes, fb);
+            }
+          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ======================================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc_bf16_f32(BM, BN);
-      bool ok = wait_bar<false>(&ss->w_full, 0, abort_flag);
-      int stage = 0; uint32_t phase = 0;
-      for (int s = kBwd ? 1 : 0; s < steps && ok; ++s) {
-        for (int kb = 0; kb < num_kb; ++kb) {
-          ok = wait_bar<false>(&ss->full[stage], phase, abort_flag);
-          if (!ok) break;
+    // whole warp, uniform control flow; one elected lane issues tcgen05.mma / tcgen05.commit
+    constexpr uint32_t idesc = tc::make_idesc_bf16_f32(BM, BN);
+    bool ok = wait_bar<false>(&ss->w_full, 0, abort_flag);
+    const uint32_t full0 = tc::smem_u32(&ss->full[0]), empty0 = tc::smem_u32(&ss->empty[0]);
+    const uint32_t tfull0 = tc::smem_u32(&ss->tmem_full[0]);
+    const uint64_t desc_a0 = tc::desc_kmajor_sw128(tc::smem_u32(smem_a));      // + stage * (kABytes >> 4)
+    const uint64_t desc_w0 = tc::desc_kmajor_sw128(tc::smem_u32(smem_w));      // + kb * (kWBlockBytes >> 4)
+    uint32_t stage = 0, phase = 0;
+    for (int s = kBwd ? 1 : 0; s < steps && ok; ++s) {
+      for (int tile = 0; tile < kTiles && ok; ++tile) {
+        const uint32_t acc = tmem_d + tile * BN;
+        uint64_t db = desc_w0;
+        for (int kb = 0; kb < num_kb; ++kb, db += (kWBlockBytes >> 4)) {
+          if (!tc::mbar_try_wait_u32(full0 + 8 * stage, phase)) {
+            ok = wait_bar<false>(&ss->full[stage], phase, abort_flag);
+            if (!ok) break;
+          }
           tc::fence_after_sync();
-          const uint64_t da = tc::desc_kmajor_sw128(tc::smem_u32(smem_a + stage * kABytes));
-          const uint64_t db = tc::desc_kmajor_sw128(tc::smem_u32(smem_w + (size_t)kb * kWBlockBytes));
-#pragma unroll
-          for (int k = 0; k < BK / UK; ++k)
-            tc::mma_bf16_ss(tmem_d, tc::desc_advance(da, k * UK * 2), tc::desc_advance(db, k * UK * 2), idesc, (kb | k) != 0);
-          if (mcast) mma_commit_mc(&ss->empty[stage], cmask); else tc::mma_commit(&ss->empty[stage]);
-          if (kb == num_kb - 1) tc::mma_commit(&ss->tmem_full);
+          if (tc::elect_one()) {
+            if (p.debug_mode == 2) {
+              tc::mbar_arrive(&ss->empty[stage]);
+              if (kb == num_kb - 1) tc::mbar_arrive(&ss->tmem_full[tile]);
+            } else {
+              const uint64_t da = desc_a0 + (uint64_t)(stage * (kABytes >> 4));
+              if (kb == 0) tc::mma_bf16_ss_first(acc, da, db, idesc); else tc::mma_bf16_ss_acc(acc, da, db, idesc);
+              tc::mma_bf16_ss_acc(acc, da + 2, db + 2, idesc);
+              tc::mma_bf16_ss_acc(acc, da + 4, db + 4, idesc);
+              tc::mma_bf16_ss_acc(acc, da + 6, db + 6, idesc);
+              tc::mma_commit_u32(empty0 + 8 * stage);
+              if (kb == num_kb - 1) tc::mma_commit_u32(tfull0 + 8 * tile);
+            }
+          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ======================================================================== epilogue: one thread = one batch row
-    const int ew = warp - kEpiWarp0;
-    const int rloc = ew * 32 + lane;
+    // ======================================================================== epilogue (one 4-warp group per batch tile)
+    const int ewi = warp - kEpiWarp0;
+    const int quarter = ewi & 3, tile = ewi >> 2;
+    const int rloc = quarter * 32 + lane;
+    const int mb = g * kTiles + tile;
     const int row = mb * BM + rloc;
     const bool valid = row < p.B;
     const int H = p.H, B = p.B;
-    const uint32_t taddr = tmem_d + ((uint32_t)(ew * 32) << 16);
+    const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + tile * BN;
+    unsigned int* counter = p.sync + mb;
+    uint64_t* tfull = &ss->tmem_full[tile];
     uint32_t tphase = 0;
     bool ok = true;
+    const bool dbg_thread = p.dbg && blockIdx.x == 0 && ewi == 0 && lane == 0;
+    auto group_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + tile) : "memory"); };
 
     if (!kBwd) {
       const int j0 = nb * 16;
+      const int n0 = nb * 64;
       for (int t = 0; t < p.T && ok; ++t) {
         // operands that do not depend on the GEMM: issue their loads before waiting on the accumulator
         uint4 gxv[8];
         float4 cv[4];
         if (valid) {
-          const __nv_bfloat16* gp = p.gx + ((size_t)t * B + row) * (4 * H) + nb * 64;
+          const __nv_bfloat16* gp = p.gx + ((size_t)t * B + row) * (4 * H) + n0;
 #pragma unroll
           for (int i = 0; i < 8; ++i) gxv[i] = ldg_nc16(gp + 8 * i);
           const float* cp = p.c_seq + ((size_t)t * B + row) * H + j0;
 #pragma unroll
           for (int i = 0; i < 4; ++i) cv[i] = *reinterpret_cast<const float4*>(cp + 4 * i);
         }
-        ok = wait_bar<false>(&ss->tmem_full, tphase, abort_flag);
+        ok = wait_bar<false>(tfull, tphase, abort_flag);
         tphase ^= 1;
         if (!ok) break;
         tc::fence_after_sync();
-        if (p.dbg && blockIdx.x == 0 && rloc == 0) p.dbg[4 * t + 1] = gtime();
-        uint32_t v0[32], v1[32];
-        tc::tmem_ld32(taddr, v0);
-        tc::tmem_ld32(taddr + 32, v1);
-        tc::tmem_ld_wait();
-        tc::fence_before_sync();
-        uint32_t hpk[8], apk[32];
+        if (dbg_thread) p.dbg[4 * t + 1] = gtime();
         float cn[16];
-        if (valid) {
+        uint32_t hpk[8];
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            const uint32_t* vv = jj < 8 ? v0 : v1;
-            const int q = (jj & 7) * 4;
-            const uint4 g4 = gxv[jj >> 1];
+        for (int pass = 0; pass < 2; ++pass) {           // 32 accumulator columns (8 hidden units) per pass
+          uint32_t v[32];
+          tc::tmem_ld32(taddr + 32 * pass, v);
+          tc::tmem_ld_wait();
+          uint32_t apk[16];
+          const float* bs = ss->bias + 32 * pass;
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const uint4 g4 = gxv[4 * pass + (jj >> 1)];
             const uint32_t ga = (jj & 1) ? g4.z : g4.x, gb = (jj & 1) ? g4.w : g4.y;
-            float pi = __uint_as_float(vv[q + 0]) + bf_lo(ga) + ss->bias[4 * jj + 0];
-            float pf = __uint_as_float(vv[q + 1]) + bf_hi(ga) + ss->bias[4 * jj + 1];
-            float pg = __uint_as_float(vv[q + 2]) + bf_lo(gb) + ss->bias[4 * jj + 2];
-            float po = __uint_as_float(vv[q + 3]) + bf_hi(gb) + ss->bias[4 * jj + 3];
-            float ig = ts::sigmoidf_fast(pi), fg = ts::sigmoidf_fast(pf), gg = ts::tanhf_fast(pg), og = ts::sigmoidf_fast(po);
-            float cprev = reinterpret_cast<const float*>(cv)[jj];
-            float c = fg * cprev + ig * gg;
-            float h = og * ts::tanhf_fast(c);
-            cn[jj] = c;
+            const float pi = __uint_as_float(v[4 * jj + 0]) + bf_lo(ga) + bs[4 * jj + 0];
+            const float pf = __uint_as_float(v[4 * jj + 1]) + bf_hi(ga) + bs[4 * jj + 1];
+            const float pg = __uint_as_float(v[4 * jj + 2]) + bf_lo(gb) + bs[4 * jj + 2];
+            const float po = __uint_as_float(v[4 * jj + 3]) + bf_hi(gb) + bs[4 * jj + 3];
+            const float ig = ts::sigmoidf_fast(pi), fg = ts::sigmoidf_fast(pf), gg = ts::tanhf_fast(pg), og = ts::sigmoidf_fast(po);
+            const float c = fg * reinterpret_cast<const float*>(cv)[8 * pass + jj] + ig * gg;
+            cn[8 * pass + jj] = c;
+            const float h = og * ts::tanhf_fast(c);
+            if (jj & 1) hpk[4 * pass + (jj >> 1)] = pack_bf2(__uint_as_float(hpk[4 * pass + (jj >> 1)]), h);
+            else hpk[4 * pass + (jj >> 1)] = __float_as_uint(h);
             apk[2 * jj] = pack_bf2(ig, fg);
             apk[2 * jj + 1] = pack_bf2(gg, og);
-            if (jj & 1) hpk[jj >> 1] = pack_bf2(__uint_as_float(hpk[jj >> 1]), h); else hpk[jj >> 1] = __float_as_uint(h);
           }
-          // h first: it is the only thing other CTAs wait for
-          __nv_bfloat16* hp = p.h_seq + ((size_t)(t + 1) * B + row) * H + j0;
-          stg16(hp, make_uint4(hpk[0], hpk[1], hpk[2], hpk[3]));
-          stg16(hp + 8, make_uint4(hpk[4], hpk[5], hpk[6], hpk[7]));
+          {
+            // next step's operand: the same 8 values into the swizzled tile image (16 B chunk c of row r sits at c ^ (r & 7))
+            const size_t blk = ((size_t)(t + 1) * p.tiles_m + mb) * (H / BK) + (j0 / BK);
+            const int chunk = ((j0 % BK) / 8 + pass) ^ (rloc & 7);
+            stg16(p.a_tiled + blk * (BM * BK) + rloc * BK + chunk * 8,
+                  make_uint4(hpk[4 * pass], hpk[4 * pass + 1], hpk[4 * pass + 2], hpk[4 * pass + 3]));
+          }
+          if (valid) {
+            // h first: it is the only thing other CTAs wait for (act is private to this thread's next backward)
+            const uint4 h8 = make_uint4(hpk[4 * pass], hpk[4 * pass + 1], hpk[4 * pass + 2], hpk[4 * pass + 3]);
+            stg16(p.h_seq + ((size_t)(t + 1) * B + row) * H + j0 + 8 * pass, h8);
+            __nv_bfloat16* ap = p.act + ((size_t)t * B + row) * (4 * H) + n0 + 32 * pass;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) stg16(ap + 8 * i, make_uint4(apk[4 * i], apk[4 * i + 1], apk[4 * i + 2], apk[4 * i + 3]));
+          }
         }
+        tc::fence_before_sync();
         __threadfence();
         asm volatile("fence.proxy.async.global;" ::: "memory");     // these rows are read next by TMA (async proxy)
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        group_bar();
         if (rloc == 0) {
           signal_counter(counter);
-          if (p.dbg && blockIdx.x == 0) p.dbg[4 * t + 2] = gtime();
+          if (dbg_thread) p.dbg[4 * t + 2] = gtime();
         }
         if (valid) {
           float* cp = p.c_seq + ((size_t)(t + 1) * B + row) * H + j0;
 #pragma unroll
           for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(cp + 4 * i) = make_float4(cn[4 * i], cn[4 * i + 1], cn[4 * i + 2], cn[4 * i + 3]);
-          __nv_bfloat16* ap = p.act + ((size_t)t * B + row) * (4 * H) + nb * 64;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) stg16(ap + 8 * i, make_uint4(apk[4 * i], apk[4 * i + 1], apk[4 * i + 2], apk[4 * i + 3]));
         }
       }
     } else {
-      const int j0 = nb * 64 + ks * 16;            // hidden columns this cluster member owns after the reduce-scatter
-      const uint32_t xbase = tc::smem_u32(smem_x);
-      const uint32_t xbar = tc::smem_u32(&ss->xchg_full);
+      // after the reduce-scatter this cluster member owns hidden [64 nb + 16 ks, +16) of this batch tile
+      const int j0 = nb * 64 + ks * 16;
+      uint8_t* xbuf = smem_x + tile * kXchgBytes;                 // [4 src][128 rows][16 bf16]
+      const uint32_t xbase = tc::smem_u32(xbuf);
+      const uint32_t xbar = tc::smem_u32(&ss->xchg_full[tile]);
       uint32_t xphase = 0;
       float dc[16], dh[16];
       if (valid) {
@@ -354,58 +411,54 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       for (int s = 0; s <= p.T && ok; ++s) {
         const int t = p.T - 1 - s;
         uint4 av[8], dhv[2];
-        float4 cpv[4], cnv[4];
         if (valid && s < p.T) {
           const __nv_bfloat16* ap = p.act + ((size_t)t * B + row) * (4 * H) + 4 * j0;
 #pragma unroll
           for (int i = 0; i < 8; ++i) av[i] = ldg_nc16(ap + 8 * i);
           const __nv_bfloat16* dp = p.dh_seq + ((size_t)t * B + row) * H + j0;
           dhv[0] = ldg_nc16(dp); dhv[1] = ldg_nc16(dp + 8);
-          const float* c0p = p.c_seq + ((size_t)t * B + row) * H + j0;
-          const float* c1p = p.c_seq + ((size_t)(t + 1) * B + row) * H + j0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { cpv[i] = *reinterpret_cast<const float4*>(c0p + 4 * i); cnv[i] = *reinterpret_cast<const float4*>(c1p + 4 * i); }
+          // the cell states come from HBM (saved by the forward pass): pull their lines into L2 now, they are
+          // consumed after the GEMM + exchange
+          prefetch_l2(p.c_seq + ((size_t)t * B + row) * H + j0);
+          prefetch_l2(p.c_seq + ((size_t)(t + 1) * B + row) * H + j0);
         }
         if (s > 0) {
-          ok = wait_bar<false>(&ss->tmem_full, tphase, abort_flag);
+          ok = wait_bar<false>(tfull, tphase, abort_flag);
           tphase ^= 1;
           if (!ok) break;
           tc::fence_after_sync();
-          if (p.dbg && blockIdx.x == 0 && rloc == 0) p.dbg[4 * s + 1] = gtime();
-          uint32_t v0[32], v1[32];
-          tc::tmem_ld32(taddr, v0);
-          tc::tmem_ld32(taddr + 32, v1);
-          tc::tmem_ld_wait();
-          tc::fence_before_sync();
-          // reduce-scatter over the 4 K-quarters: chunk q (16 columns) belongs to cluster member q
+          if (dbg_thread) p.dbg[4 * s + 1] = gtime();
+          // reduce-scatter over the 4 K-quarters: column chunk q (16 wide, bf16) goes to member q's slot [ks] (DSMEM)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t* src = q < 2 ? v0 + 16 * q : v1 + 16 * (q - 2);
-            if (q == ks) {
+          for (int pass = 0; pass < 2; ++pass) {
+            uint32_t v[32];
+            tc::tmem_ld32(taddr + 32 * pass, v);
+            tc::tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) dh[i] = __uint_as_float(src[i]);
-            } else {
-              const int slot = ks < q ? ks : ks - 1;                      // my index among q's three foreign sources
-              const uint32_t dst = mapa(xbase + (uint32_t)((slot * BM + rloc) * 64), (uint32_t)q);
+            for (int qq = 0; qq < 2; ++qq) {
+              const uint32_t dst = mapa(xbase + (uint32_t)((ks * BM + rloc) * 32), (uint32_t)(2 * pass + qq));
+              uint32_t pk[8];
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                st_cluster_f4(dst + 16 * i, make_float4(__uint_as_float(src[4 * i]), __uint_as_float(src[4 * i + 1]),
-                                                       __uint_as_float(src[4 * i + 2]), __uint_as_float(src[4 * i + 3])));
+              for (int i = 0; i < 8; ++i) pk[i] = pack_bf2(__uint_as_float(v[16 * qq + 2 * i]), __uint_as_float(v[16 * qq + 2 * i + 1]));
+              st_cluster_u4(dst, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+              st_cluster_u4(dst + 16, make_uint4(pk[4], pk[5], pk[6], pk[7]));
             }
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (rloc < 4 && rloc != ks) mbar_arrive_remote(mapa(xbar, (uint32_t)rloc));
-          ok = wait_bar<true>(&ss->xchg_full, xphase, abort_flag);
+          tc::fence_before_sync();
+          group_bar();
+          if (rloc < 4) mbar_arrive_remote(mapa(xbar, (uint32_t)rloc));
+          ok = wait_bar<true>(&ss->xchg_full[tile], xphase, abort_flag);
           xphase ^= 1;
           if (!ok) break;
 #pragma unroll
-          for (int src = 0; src < 3; ++src) {
-            const float4* xp = reinterpret_cast<const float4*>(smem_x + (size_t)(src * BM + rloc) * 64);
+          for (int i = 0; i < 16; ++i) dh[i] = 0.f;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float4 x4 = xp[i];
-              dh[4 * i] += x4.x; dh[4 * i + 1] += x4.y; dh[4 * i + 2] += x4.z; dh[4 * i + 3] += x4.w;
-            }
+          for (int src = 0; src < 4; ++src) {
+            const uint4* xp = reinterpret_cast<const uint4*>(xbuf + (size_t)(src * BM + rloc) * 32);
+            const uint4 x0 = xp[0], x1 = xp[1];
+            const uint32_t w[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { dh[2 * i] += bf_lo(w[i]); dh[2 * i + 1] += bf_hi(w[i]); }
           }
         }
         if (s == p.T) {
@@ -418,35 +471,49 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           }
           break;
         }
-        uint32_t gpk[32];
         if (valid) {
-#pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            const uint4 a4 = av[jj >> 1];
-            const uint32_t aa = (jj & 1) ? a4.z : a4.x, ab = (jj & 1) ? a4.w : a4.y;
-            const float ig = bf_lo(aa), fg = bf_hi(aa), gg = bf_lo(ab), og = bf_hi(ab);
-            const uint4 d4 = dhv[jj >> 3];
-            const uint32_t dw = ((jj >> 1) & 3) == 0 ? d4.x : ((jj >> 1) & 3) == 1 ? d4.y : ((jj >> 1) & 3) == 2 ? d4.z : d4.w;
-            const float dht = dh[jj] + ((jj & 1) ? bf_hi(dw) : bf_lo(dw));
-            const float cprev = reinterpret_cast<const float*>(cpv)[jj];
-            const float tcn = ts::tanhf_fast(reinterpret_cast<const float*>(cnv)[jj]);
-            const float dct = dc[jj] + dht * og * (1.f - tcn * tcn);
-            const float d_o = dht * tcn, d_i = dct * gg, d_f = dct * cprev, d_g = dct * ig;
-            dc[jj] = dct * fg;
-            gpk[2 * jj] = pack_bf2(d_i * ig * (1.f - ig), d_f * fg * (1.f - fg));
-            gpk[2 * jj + 1] = pack_bf2(d_g * (1.f - gg * gg), d_o * og * (1.f - og));
-            dh[jj] = 0.f;
-          }
+          const float* c0p = p.c_seq + ((size_t)t * B + row) * H + j0;
+          const float* c1p = p.c_seq + ((size_t)(t + 1) * B + row) * H + j0;
           __nv_bfloat16* gp = p.dpre + ((size_t)t * B + row) * (4 * H) + 4 * j0;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) stg16(gp + 8 * i, make_uint4(gpk[4 * i], gpk[4 * i + 1], gpk[4 * i + 2], gpk[4 * i + 3]));
+          for (int pass = 0; pass < 2; ++pass) {
+            float4 cpv[2], cnv[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) { cpv[i] = *reinterpret_cast<const float4*>(c0p + 8 * pass + 4 * i); cnv[i] = *reinterpret_cast<const float4*>(c1p + 8 * pass + 4 * i); }
+            uint32_t gpk[16];
+#pragma unroll
+            for (int j8 = 0; j8 < 8; ++j8) {
+              const int jj = 8 * pass + j8;
+              const uint4 a4 = av[jj >> 1];
+              const uint32_t aa = (jj & 1) ? a4.z : a4.x, ab = (jj & 1) ? a4.w : a4.y;
+              const float ig = bf_lo(aa), fg = bf_hi(aa), gg = bf_lo(ab), og = bf_hi(ab);
+              const uint4 d4 = dhv[pass];
+              const uint32_t dw = (j8 >> 1) == 0 ? d4.x : (j8 >> 1) == 1 ? d4.y : (j8 >> 1) == 2 ? d4.z : d4.w;
+              const float dht = dh[jj] + ((jj & 1) ? bf_hi(dw) : bf_lo(dw));
+              const float cprev = reinterpret_cast<const float*>(cpv)[j8];
+              const float tcn = ts::tanhf_fast(reinterpret_cast<const float*>(cnv)[j8]);
+              const float dct = dc[jj] + dht * og * (1.f - tcn * tcn);
+              const float d_o = dht * tcn, d_i = dct * gg, d_f = dct * cprev, d_g = dct * ig;
+              dc[jj] = dct * fg;
+              gpk[2 * j8] = pack_bf2(d_i * ig * (1.f - ig), d_f * fg * (1.f - fg));
+              gpk[2 * j8 + 1] = pack_bf2(d_g * (1.f - gg * gg), d_o * og * (1.f - og));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) stg16(gp + 32 * pass + 8 * i, make_uint4(gpk[4 * i], gpk[4 * i + 1], gpk[4 * i + 2], gpk[4 * i + 3]));
+            // next iteration's operand: this thread's 64 gate columns are exactly row rloc of k-block j0/16
+            const size_t blk = ((size_t)t * p.tiles_m + mb) * (4 * H / BK) + (j0 / 16);
+            __nv_bfloat16* tp = p.a_tiled + blk * (BM * BK) + rloc * BK;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              stg16(tp + (((4 * pass + i) ^ (rloc & 7)) * 8), make_uint4(gpk[4 * i], gpk[4 * i + 1], gpk[4 * i + 2], gpk[4 * i + 3]));
+          }
         }
         __threadfence();
         asm volatile("fence.proxy.async.global;" ::: "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        group_bar();
         if (rloc == 0) {
           signal_counter(counter);
-          if (p.dbg && blockIdx.x == 0) p.dbg[4 * s + 2] = gtime();
+          if (dbg_thread) p.dbg[4 * s + 2] = gtime();
         }
       }
     }
@@ -454,104 +521,108 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
   tc::fence_before_sync();
   __syncthreads();
-  if (kCluster > 1) cluster_sync_all();          // nobody exits while a peer may still multicast into / arrive on its smem
+  if (kBwd) cluster_sync_all();                  // nobody exits while a peer may still write into / arrive on its smem
   if (threadIdx.x == 0 && ss->abort_flag) atomicExch(reinterpret_cast<int*>(p.sync + 63), 1);
-  if (warp == 2) tc::tmem_dealloc(tmem_d, 64);
+  if (warp == 2) tc::tmem_dealloc(tmem_d, kTmemCols);
 }
 
-size_t smem_bytes(int H, bool bwd) {
-  return (size_t)(H / BK) * kWBlockBytes + kStages * kABytes + (bwd ? kXchgBytes : 0) + sizeof(SeqSmem) + 1024;
+size_t smem_bytes(int H, bool bwd, int stages, int tiles) {
+  return (size_t)(H / BK) * kWBlockBytes + (size_t)stages * kABytes + (bwd ? tiles * kXchgBytes : 0) + sizeof(SeqSmem) + 1024;
 }
 
-template <bool kBwd, int kCluster>
-int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tw, const SeqParams& p, int grid, size_t smem, bool dry, cudaStream_t st) {
-  auto kern = lstm_seq_kernel<kBwd, kCluster>;
+template <bool kBwd, int kTiles, int kStages>
+int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tw, const SeqParams& p, int grid, cudaStream_t st) {
+  auto kern = lstm_seq_kernel<kBwd, kTiles, kStages>;
+  const size_t smem = smem_bytes(p.H, kBwd, kStages, kTiles);
+  if (smem > 227 * 1024) return -4;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  if (kCluster > 8) {
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e != cudaSuccess) return (int)e;
-  }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128 + 128 * kTiles); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = kCluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[0].val.clusterDim.x = kBwd ? 4 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  if (kCluster > 1) {
+  if (kBwd) {
     int nclusters = 0;
     e = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
     if (e != cudaSuccess) { cudaGetLastError(); return -20; }
-    if (nclusters * kCluster < grid) return -21;              // not co-resident with this cluster size
+    if (nclusters * 4 < grid) return -21;              // not co-resident
   }
-  if (dry) return 0;
   e = cudaLaunchKernelEx(&cfg, kern, ta, tw, p);
   return (int)e;
 }
 
-int g_fwd_cluster = -1;   // resolved once: largest multicast cluster that is co-resident for the current shape
-int g_fwd_cluster_key = 0;
+template <bool kBwd>
+int dispatch(const CUtensorMap& ta, const CUtensorMap& tw, const SeqParams& p, int grid, int tiles, int stages, cudaStream_t st) {
+  if (tiles == 2) {
+    if (stages == 3) return launch_cfg<kBwd, 2, 3>(ta, tw, p, grid, st);
+    if (stages == 4) return launch_cfg<kBwd, 2, 4>(ta, tw, p, grid, st);
+    if (stages == 5) return launch_cfg<kBwd, 2, 5>(ta, tw, p, grid, st);
+    if (stages == 6) return launch_cfg<kBwd, 2, 6>(ta, tw, p, grid, st);
+  } else {
+    if (stages == 3) return launch_cfg<kBwd, 1, 3>(ta, tw, p, grid, st);
+    if (stages == 4) return launch_cfg<kBwd, 1, 4>(ta, tw, p, grid, st);
+    if (stages == 5) return launch_cfg<kBwd, 1, 5>(ta, tw, p, grid, st);
+    if (stages == 6) return launch_cfg<kBwd, 1, 6>(ta, tw, p, grid, st);
+  }
+  return -5;
+}
+
+int pick_stages(int H, bool bwd, int tiles) {
+  for (int s = 6; s >= 3; --s)
+    if (smem_bytes(H, bwd, s, tiles) <= 227 * 1024) return s;
+  return 0;
+}
 
 }  // namespace
 
 // sync_ws: >= 64 u32; [0..tiles_m) step counters (zeroed by the caller before every launch), [63] sticky error flag.
-// cluster: requested multicast cluster size for the forward kernel (1,2,4,8; 0 = auto: largest that is co-resident).
-extern "C" int ts_lstm_seq_fwd(const void* gx, const void* w_h, const float* bias, const void* h_seq, const float* c_seq,
-                               void* act, float*, void* dbg, void*, int T, int B, int H, unsigned int* sync_ws, int cluster,
-                               cudaStream_t st) {
-  SeqParams p{};
-  p.gx = (const __nv_bfloat16*)gx; p.bias = bias; p.h_seq = (__nv_bfloat16*)h_seq; p.c_seq = (float*)c_seq;
-  p.act = (__nv_bfloat16*)act; p.sync = sync_ws; p.T = T; p.B = B; p.H = H; p.dbg = (unsigned long long*)dbg;
+// variant (tuning knob, 0 = defaults) = tiles_per_cta + 16*stages:  tiles_per_cta 0 -> 2 when the batch has an even
+// number of 128-row tiles, else 1;  stages 0 -> deepest ring that fits next to the resident weight slice.
+template <bool kBwd>
+static int seq_common(SeqParams& p, const void* a_base, uint64_t a_t, const void* w_base, int variant, cudaStream_t st) {
+  (void)a_base; (void)a_t;
+  const int H = p.H, B = p.B;
   if (H % 64 != 0) { ts::set_last_error("lstm_seq: H must be a multiple of 64"); return -2; }
-  const int tiles_m = (B + BM - 1) / BM, tiles_n = 4 * H / BN;
+  const int tiles_m = (B + BM - 1) / BM, tiles_n = kBwd ? (H / BN) * 4 : 4 * H / BN;
+  int tiles = variant & 15, stages = (variant >> 4) & 15;
+  p.debug_mode = (variant >> 12) & 3;
+  if (tiles == 0) tiles = 1;
+  if (tiles == 2 && tiles_m % 2 != 0) tiles = 1;
   int dev = 0;
   cudaGetDevice(&dev);
-  if (tiles_m * tiles_n > ts::sm_count(dev)) { ts::set_last_error("lstm_seq: grid exceeds SM count (not co-resident)"); return -3; }
-  const size_t smem = smem_bytes(H, false);
-  if (smem > 227 * 1024) { ts::set_last_error("lstm_seq: weight slice does not fit in shared memory"); return -4; }
+  const int grid = (tiles_m / tiles) * tiles_n;
+  if (grid > ts::sm_count(dev)) { ts::set_last_error("lstm_seq: grid exceeds SM count (not co-resident)"); return -3; }
+  if (stages == 0) stages = pick_stages(H, kBwd, tiles);
+  if (stages == 0 || smem_bytes(H, kBwd, stages, tiles) > 227 * 1024) { ts::set_last_error("lstm_seq: weight slice does not fit in shared memory"); return -4; }
+  const int K = kBwd ? 4 * H : H, N = kBwd ? H : 4 * H;
   CUtensorMap ta, tw;
-  if (int rc = ts::make_tmap_3d_bf16(&ta, h_seq, (uint64_t)H, (uint64_t)B, (uint64_t)T + 1, (uint64_t)H, (uint64_t)H * B, BK, BM, 1)) return rc;
-  if (int rc = ts::make_tmap_2d_bf16(&tw, w_h, (uint64_t)4 * H, (uint64_t)H, (uint64_t)H, BK, BN)) return rc;
+  if (int rc = ts::make_tmap_2d_bf16(&tw, w_base, (uint64_t)N, (uint64_t)K, (uint64_t)K, BK, BN)) return rc;
+  ta = tw;                                     // the streamed operand no longer goes through a tensor map
   p.tiles_n = tiles_n;
-  const int grid = tiles_m * tiles_n;
-  int c = cluster;
-  if (c == 0) {
-    const int key = H * 1024 + tiles_m;
-    if (g_fwd_cluster < 0 || g_fwd_cluster_key != key) {
-      g_fwd_cluster = 1; g_fwd_cluster_key = key;
-      if (tiles_n % 8 == 0 && launch_cfg<false, 8>(ta, tw, p, grid, smem, true, st) == 0) g_fwd_cluster = 8;
-      else if (tiles_n % 4 == 0 && launch_cfg<false, 4>(ta, tw, p, grid, smem, true, st) == 0) g_fwd_cluster = 4;
-      else if (tiles_n % 2 == 0 && launch_cfg<false, 2>(ta, tw, p, grid, smem, true, st) == 0) g_fwd_cluster = 2;
-    }
-    c = g_fwd_cluster;
-  }
-  if (c > 1 && tiles_n % c != 0) c = 1;
-  switch (c) {
-    case 8: return launch_cfg<false, 8>(ta, tw, p, grid, smem, false, st);
-    case 4: return launch_cfg<false, 4>(ta, tw, p, grid, smem, false, st);
-    case 2: return launch_cfg<false, 2>(ta, tw, p, grid, smem, false, st);
-    default: return launch_cfg<false, 1>(ta, tw, p, grid, smem, false, st);
-  }
+  p.tiles_m = tiles_m;
+  int rc = dispatch<kBwd>(ta, tw, p, grid, tiles, stages, st);
+  if (rc == -21) ts::set_last_error("lstm_seq_bwd: clusters of 4 are not co-resident on this device");
+  return rc;
+}
+
+extern "C" int ts_lstm_seq_fwd(const void* gx, const void* w_h, const float* bias, const void* h_seq, const float* c_seq,
+                               void* act, float*, void* dbg, void* a_tiled, int T, int B, int H, unsigned int* sync_ws, int variant,
+                               cudaStream_t st) {
+  SeqParams p{};
+  p.a_tiled = (__nv_bfloat16*)a_tiled;
+  p.gx = (const __nv_bfloat16*)gx; p.bias = bias; p.h_seq = (__nv_bfloat16*)h_seq; p.c_seq = (float*)c_seq;
+  p.act = (__nv_bfloat16*)act; p.sync = sync_ws; p.T = T; p.B = B; p.H = H; p.dbg = (unsigned long long*)dbg;
+  return seq_common<false>(p, h_seq, (uint64_t)T + 1, w_h, variant, st);
 }
 
 extern "C" int ts_lstm_seq_bwd(const void* dh_seq, const void* w_hT, const void* act, const float* c_seq, const void* dpre,
-                               float* dh0, float* dc0, void* dbg, void*, int T, int B, int H, unsigned int* sync_ws, int,
+                               float* dh0, float* dc0, void* dbg, void* a_tiled, int T, int B, int H, unsigned int* sync_ws, int variant,
                                cudaStream_t st) {
   SeqParams p{};
+  p.a_tiled = (__nv_bfloat16*)a_tiled;
   p.dh_seq = (const __nv_bfloat16*)dh_seq; p.act = (__nv_bfloat16*)act; p.c_seq = (float*)c_seq; p.dpre = (__nv_bfloat16*)dpre;
   p.dh0 = dh0; p.dc0 = dc0; p.sync = sync_ws; p.T = T; p.B = B; p.H = H; p.dbg = (unsigned long long*)dbg;
-  if (H % 64 != 0) { ts::set_last_error("lstm_seq: H must be a multiple of 64"); return -2; }
-  const int tiles_m = (B + BM - 1) / BM, tiles_n = (H / BN) * 4;        // (nb2, ks)
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (tiles_m * tiles_n > ts::sm_count(dev)) { ts::set_last_error("lstm_seq: grid exceeds SM count (not co-resident)"); return -3; }
-  const size_t smem = smem_bytes(H, true);
-  if (smem > 227 * 1024) { ts::set_last_error("lstm_seq: weight slice does not fit in shared memory"); return -4; }
-  CUtensorMap ta, tw;
-  if (int rc = ts::make_tmap_3d_bf16(&ta, dpre, (uint64_t)4 * H, (uint64_t)B, (uint64_t)T, (uint64_t)4 * H, (uint64_t)4 * H * B, BK, BM, 1)) return rc;
-  if (int rc = ts::make_tmap_2d_bf16(&tw, w_hT, (uint64_t)H, (uint64_t)4 * H, (uint64_t)4 * H, BK, BN)) return rc;
-  p.tiles_n = tiles_n;
-  int rc = launch_cfg<true, 4>(ta, tw, p, tiles_m * tiles_n, smem, false, st);
-  if (rc == -21) ts::set_last_error("lstm_seq_bwd: clusters of 4 are not co-resident on this device");
-  return rc;
+  return seq_common<true>(p, dpre, (uint64_t)T, w_hT, variant, st);
 }

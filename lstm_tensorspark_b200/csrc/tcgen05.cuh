@@ -12,6 +12,15 @@ namespace tc {
 
 TC_DEVICE uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 TC_DEVICE uint32_t lane_id() { return threadIdx.x & 31; }
+// One lane of the (fully converged) warp.  Role loops run with ALL 32 lanes in uniform control flow and issue the
+// async instructions under this predicate: then ptxas keeps descriptors / addresses in uniform registers.  Inside an
+// `if (lane == 0)` region it cannot prove uniformity and wraps every UTCHMMA / UBLKCP / UTCBAR in an
+// ELECT + R2UR.BROADCAST waterfall loop (measured: ~500 cycles per k-block instead of ~230).
+TC_DEVICE bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 
 // ---------------------------------------------------------------------------------------- mbarrier
 TC_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {
@@ -106,6 +115,50 @@ TC_DEVICE void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr) : "memory");
 }
 TC_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------- lean (u32-address) forms
+// The producer / MMA-issuer roles are ONE thread each: their scalar instruction stream is the critical path of a
+// small-tile pipeline (measured: 56 cycles per tcgen05.mma in a bare loop, ~150 once the loop re-derives descriptors,
+// converts generic->shared addresses and spills around "memory"-clobbered asm).  These variants take precomputed
+// shared-memory addresses / descriptors and carry no clobbers that are not needed for ordering.
+TC_DEVICE bool mbar_try_wait_u32(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+TC_DEVICE void mbar_expect_tx_u32(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+TC_DEVICE void bulk_load_1d_u32(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"((uint64_t)gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+TC_DEVICE void tma_load_2d_u32(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+TC_DEVICE void mma_commit_u32(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// accumulate variants with a compile-time predicate (no runtime setp operand)
+TC_DEVICE void mma_bf16_ss_acc(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.eq.u32 p, 1, 1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc));
+}
+TC_DEVICE void mma_bf16_ss_first(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.eq.u32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc));
+}
 
 // ---------------------------------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor (64 bit): [0,14) addr>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1

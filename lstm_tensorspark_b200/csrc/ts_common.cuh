@@ -8,12 +8,13 @@
 
 namespace ts {
 
-TS_DEVICE float sigmoidf_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 TS_DEVICE float tanhf_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// sigmoid(x) = 0.5*tanh(0.5x)+0.5 : ONE MUFU op (tanh.approx) instead of ex2 + rcp
+TS_DEVICE float sigmoidf_fast(float x) { return fmaf(0.5f, tanhf_fast(0.5f * x), 0.5f); }
 // accurate variants for the fp32 parity path
 TS_DEVICE float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 

@@ -18,7 +18,7 @@ from .cuda_ext import ext
 _SYNC_WS = {}
 _SM_COUNT = {}
 FORCE_GENERIC = os.environ.get("LSTM_TS_FORCE_GENERIC", "0") == "1"
-FWD_CLUSTER = int(os.environ.get("LSTM_TS_FWD_CLUSTER", "0"))     # 0 = auto (largest co-resident multicast cluster)
+SEQ_VARIANT = int(os.environ.get("LSTM_TS_SEQ_VARIANT", "0"))     # tuning knob: tiles_per_cta + 16*stages (0 = auto)
 USE_TC_GEMM = os.environ.get("LSTM_TS_TC_GEMM", "1") == "1"
 STATS = {"fast_fwd": 0, "fast_bwd": 0, "generic_fwd": 0, "generic_bwd": 0, "tc_gemm": 0, "kernels": 0}
 
@@ -48,10 +48,10 @@ def fast_path_supported(B: int, H: int, dtype: torch.dtype, device) -> bool:
     if FORCE_GENERIC or dtype != torch.bfloat16 or H % 64 != 0:
         return False
     tiles_m = (B + 127) // 128
-    tiles_n = H // 16
-    if tiles_m * tiles_n > _sms(device):
+    tiles_per_cta = 2 if tiles_m % 2 == 0 else 1      # a CTA alternates two batch tiles when it can (see the kernel)
+    if (tiles_m // tiles_per_cta) * (H // 16) > _sms(device):
         return False
-    smem = H * 64 * 2 + 4 * 16384 + 24576 + 2048   # resident slice + 4 stages + DSMEM exchange (+ barriers)
+    smem = H * 64 * 2 + 4 * 16384 + tiles_per_cta * 16384 + 2048   # resident slice + >=4 stages + DSMEM exchange
     return smem <= 227 * 1024 and tiles_m <= 16
 
 
@@ -89,7 +89,7 @@ class _LSTMSeqFn(torch.autograd.Function):
         c0f = c0.detach().float().contiguous()
         h0c = h0.detach().to(cd).contiguous()
         if fast:
-            h_seq, c_seq, act = E.lstm_seq_fwd(gx, w_h_c, bias_f, h0c, c0f, _sync_ws(x_seq.device), FWD_CLUSTER)
+            h_seq, c_seq, act = E.lstm_seq_fwd(gx, w_h_c, bias_f, h0c, c0f, _sync_ws(x_seq.device), SEQ_VARIANT)
             STATS["fast_fwd"] += 1
             STATS["kernels"] += 1
         else:
@@ -125,7 +125,7 @@ class _LSTMSeqFn(torch.autograd.Function):
         dhT = torch.zeros(B, H, dtype=torch.float32, device=dev)
         if ctx.fast:
             w_hT = w_h_c.t().contiguous()
-            dpre, dh0, dc0 = E.lstm_seq_bwd(dh_seq, w_hT, act, c_seq, dhT, dcT, _sync_ws(dev), 0)
+            dpre, dh0, dc0 = E.lstm_seq_bwd(dh_seq, w_hT, act, c_seq, dhT, dcT, _sync_ws(dev), SEQ_VARIANT)
             STATS["fast_bwd"] += 1
             STATS["kernels"] += 1
         else:
