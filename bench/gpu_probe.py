@@ -188,7 +188,7 @@ def check_seq_tune():
         bias = torch.zeros(4 * H, device=dev)
         h0 = torch.zeros(B, H, device=dev).bfloat16(); c0 = torch.zeros(B, H, device=dev)
         ws = cuda_lstm._sync_ws(dev)
-        for (tiles, st, mode) in ((1, 4, 0), (1, 6, 0), (1, 4, 1), (1, 4, 2), (2, 6, 0)):
+        for (tiles, st, mode) in ((1, 4, 0), (1, 6, 0), (1, 6, 1), (1, 6, 2)):
             v = tiles + 16 * st + 4096 * mode
             try:
                 ms = _time_ms(lambda: E.lstm_seq_fwd(gx, whb, bias, h0, c0, ws, v), iters=5, warm=2)
@@ -203,7 +203,15 @@ def check_seq_tune():
                 t0 = int(d[0, 0])
                 issue = [(int(x) - t0) for x in kb[:nk]]
                 landed = [(int(x) - t0) for x in kb[32:32 + nk]]
+                w3 = dbg[:4 * (T + 2)].view(-1, 4)[8:24, 3].cpu()
+                mma_first = [int(x) & 0xFFFFF for x in w3]
+                mma_wait = [(int(x) >> 20) & 0xFFFFF for x in w3]
+                mma_total = [(int(x) >> 40) & 0xFFFFF for x in w3]
+                e = dbg[4 * (T + 2):4 * (T + 2) + 3].cpu()
+                acc8, sig8 = int(d[0, 1]), int(d[0, 2])
                 _emit("fwd_variant", T=T, B=B, H=H, tiles=tiles, stages=st, debug_mode=mode, us_per_step=ms * 1e3 / T,
+                      mma_first_wait_cyc=sum(mma_first) / 16, mma_later_wait_cyc=sum(mma_wait) / 16, mma_step_cyc=sum(mma_total) / 16,
+                      epi_ld_ns=int(e[0]) - acc8, epi_math_store_ns=int(e[1]) - int(e[0]), epi_bar_ns=int(e[2]) - int(e[1]), epi_signal_ns=sig8 - int(e[2]),
                       load_mma_us=float((accum - waited).float().mean()) / 1e3, epi_us=float((sig - accum).float().mean()) / 1e3,
                       sync_us=float((waited[1:] - sig[:-1]).float().mean()) / 1e3, 
                       accum_ns=int(d[0, 1]) - t0)

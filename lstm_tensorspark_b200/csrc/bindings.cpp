@@ -30,8 +30,8 @@ int ts_fused_allreduce(const unsigned long long*, unsigned long long, unsigned l
 int ts_ar_max_blocks();
 int ts_ar_flag_words();
 int ts_gemm_bf16_tn(const void*, const void*, void*, const float*, int, int, int, int, int, int, cudaStream_t);
-int ts_lstm_seq_fwd(const void*, const void*, const float*, const void*, const float*, void*, float*, void*, void*, int,
-                    int, int, unsigned int*, int, cudaStream_t);
+int ts_lstm_seq_fwd(const void*, const void*, const float*, const void*, const float*, void*, const float*, void*, void*, int,
+                    int, int, unsigned int*, int, cudaStream_t, const void*);
 int ts_lstm_seq_bwd(const void*, const void*, const void*, const float*, const void*, float*, float*, void*, void*, int,
                     int, int, unsigned int*, int, cudaStream_t);
 int ts_umma_bench(int, int, int, int, long long*, cudaStream_t);
@@ -186,25 +186,14 @@ std::vector<Tensor> lstm_seq_fwd(const Tensor& gx, const Tensor& w_h, const Tens
   auto h_seq = torch::empty({T + 1, B, H}, gx.options());
   auto c_seq = torch::empty({T + 1, B, H}, c0.options());
   auto act = torch::empty({T, B, 4 * H}, gx.options());
-  h_seq[0].copy_(h0);
-  c_seq[0].copy_(c0);
-  sync_ws.narrow(0, 0, 16).zero_();       // step counters restart at 0 every launch; [63] = sticky error flag
-  // streamed-operand images: [T+1][tiles_m][H/64][128][64] bf16, 128B-swizzled; slot 0 = h0
+  // streamed-operand images: [T+1][tiles_m][H/64][128][64] bf16, 128B-swizzled; slot 0 (= h0) and h_seq[0] / c_seq[0] /
+  // the step counters are written by the launcher's prologue kernel
   const int tiles_m = (B + 127) / 128, nkb = H / 64;
   auto tiled = torch::empty({(int64_t)(T + 1), tiles_m, nkb, 128, 64}, gx.options());
-  {
-    auto hp = torch::zeros({tiles_m * 128, H}, gx.options());
-    hp.narrow(0, 0, B).copy_(h0);
-    auto v = hp.view({tiles_m, 128, nkb, 8, 8}).permute({0, 2, 1, 3, 4});            // [tm, kb, r, chunk, 8]
-    auto r = torch::arange(128, torch::TensorOptions().device(gx.device()).dtype(torch::kInt64)).remainder(8).view({128, 1});
-    auto c = torch::arange(8, torch::TensorOptions().device(gx.device()).dtype(torch::kInt64)).view({1, 8});
-    auto src = c.bitwise_xor(r);                                                       // position p holds chunk p ^ (r&7)
-    auto idx = src.view({1, 1, 128, 8, 1}).expand({tiles_m, nkb, 128, 8, 8});
-    tiled[0].copy_(v.gather(3, idx).reshape({tiles_m, nkb, 128, 64}));
-  }
+  TORCH_CHECK(h0.scalar_type() == torch::kBFloat16 && c0.scalar_type() == torch::kFloat32, "h0 bf16 / c0 fp32");
   check(ts_lstm_seq_fwd(gx.data_ptr(), w_h.data_ptr(), bias.data_ptr<float>(), h_seq.data_ptr(), c_seq.data_ptr<float>(),
-                        act.data_ptr(), nullptr, dbg.has_value() ? dbg->data_ptr() : nullptr, tiled.data_ptr(), T, B, H,
-                        (unsigned int*)sync_ws.data_ptr<int>(), (int)variant, stream()), "lstm_seq_fwd");
+                        act.data_ptr(), c0.data_ptr<float>(), dbg.has_value() ? dbg->data_ptr() : nullptr, tiled.data_ptr(), T, B, H,
+                        (unsigned int*)sync_ws.data_ptr<int>(), (int)variant, stream(), h0.data_ptr()), "lstm_seq_fwd");
   return {h_seq, c_seq, act};
 }
 
@@ -220,7 +209,6 @@ std::vector<Tensor> lstm_seq_bwd(const Tensor& dh_seq, const Tensor& w_hT, const
   auto dpre = torch::empty_like(act);
   auto dh0 = dhT.clone();
   auto dc0 = dcT.clone();
-  sync_ws.narrow(0, 0, 16).zero_();
   const int tiles_m = (B + 127) / 128;
   auto tiled = torch::empty({(int64_t)T, tiles_m, 4 * H / 64, 128, 64}, act.options());   // dG images, written by the kernel
   check(ts_lstm_seq_bwd(dh_seq.data_ptr(), w_hT.data_ptr(), act.data_ptr(), c_seq.data_ptr<float>(), dpre.data_ptr(),

@@ -41,7 +41,7 @@ constexpr int kMaxStages = 8;
 constexpr int kEpiWarp0 = 4;
 constexpr int kABytes = BM * BK * 2;          // 16 KB
 constexpr int kWBlockBytes = BN * BK * 2;     // 8 KB per 64-wide K block
-constexpr int kXchgBytes = 4 * BM * 16 * 2;   // backward, per batch tile: 4 source slots of [128 x 16] bf16 partial chunks
+constexpr int kXchgBytes = 4 * BM * 16 * 2;   // backward: 4 source slots of [128 x 16] bf16 partial chunks
 constexpr long long kSpinLimit = 6000000000LL;   // ~3 s of SM clocks: a bug surfaces as an error, not a hung GPU
 
 struct SeqSmem {
@@ -164,57 +164,55 @@ struct SeqParams {
 };
 
 // Work decomposition
-//   forward : CTA (g, nb)      -> gate columns [64 nb, +64) = hidden [16 nb, +16), K = H, for the kTiles batch tiles
-//                                 mb = g*kTiles + tile.  With kTiles = 2 a CTA ALTERNATES two independent batch tiles:
-//                                 the epilogue + grid-barrier latency of one tile hides under the operand stream of the
-//                                 other, and the weight slice is shared, so the operand replication (the L2->SM fabric
-//                                 traffic that bounds the step) halves.
-//   backward: CTA (g, nb2, ks) -> partial dh columns [64 nb2, +64) over gate-column quarter ks (K = H); the 4 ks form a
+//   forward : CTA (mb, nb)      -> gate columns [64 nb, +64) = hidden [16 nb, +16) of batch tile mb, K = H.
+//   backward: CTA (mb, nb2, ks) -> partial dh columns [64 nb2, +64) over gate-column quarter ks (K = H); the 4 ks form a
 //                                 cluster; after the DSMEM reduce-scatter member ks owns hidden [64 nb2 + 16 ks, +16).
-// Warps: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, then 4 epilogue warps per batch tile
-// (warp % 4 = TMEM lane quarter; one thread = one batch row, 64 accumulator columns in two passes of 32).
-template <bool kBwd, int kTiles, int kStages>
-__global__ void __launch_bounds__(128 + 128 * kTiles, 1)
-lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                const SeqParams p) {
+// Warps: 0 = producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, 4..11 = epilogue (warp % 4 = TMEM lane quarter,
+// (warp-4)/4 = which 32 of the 64 accumulator columns; one thread = one batch row x 8 hidden units).
+// The two role warps run CONVERGED and issue under elect.sync so descriptors / addresses stay in uniform registers;
+// k-blocks are handled in pairs (two overlapped mbarrier.try_wait, 8 MMAs per turn): the barrier turn-around, not the
+// tensor pipe (48 cycles per M128xN64xK16 instruction), is what bounds a step.
+template <bool kBwd, int kStages>
+__global__ void __launch_bounds__(384, 1)
+lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int num_kb = p.H / BK;
   uint8_t* smem_w = smem;                                    // resident weight slice: num_kb blocks of [64 x 64]
   uint8_t* smem_a = smem + (size_t)num_kb * kWBlockBytes;    // kStages x 16 KB
-  uint8_t* smem_x = smem_a + kStages * kABytes;              // backward: DSMEM exchange buffers (bf16), one per tile
-  SeqSmem* ss = reinterpret_cast<SeqSmem*>(smem_x + (kBwd ? kTiles * kXchgBytes : 0));
+  uint8_t* smem_x = smem_a + kStages * kABytes;              // backward: DSMEM exchange buffer (bf16)
+  SeqSmem* ss = reinterpret_cast<SeqSmem*>(smem_x + (kBwd ? kXchgBytes : 0));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = blockIdx.x / p.tiles_n;                      // batch-tile group
-  const int in_g = blockIdx.x % p.tiles_n;
+  const int mb = blockIdx.x / p.tiles_n;
+  const int in_mb = blockIdx.x % p.tiles_n;
   const uint32_t crank = kBwd ? cluster_ctarank() : 0;
-  const int nb = kBwd ? in_g / 4 : in_g;
+  const int nb = kBwd ? in_mb / 4 : in_mb;
   const int ks = kBwd ? (int)crank : 0;
+  unsigned int* counter = p.sync + mb;
   volatile int* abort_flag = &ss->abort_flag;
   const int steps = kBwd ? p.T + 1 : p.T;                    // backward runs one extra GEMM to produce dh_0
-  constexpr int kTmemCols = kTiles == 2 ? 128 : 64;
 
   if (threadIdx.x == 0) {
     ss->abort_flag = 0;
-    tc::prefetch_tmap(&tmap_a);
     tc::prefetch_tmap(&tmap_w);
     for (int s = 0; s < kStages; ++s) { tc::mbar_init(&ss->full[s], 1); tc::mbar_init(&ss->empty[s], 1); }
     tc::mbar_init(&ss->w_full, 1);
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&ss->tmem_full[i], 1); tc::mbar_init(&ss->xchg_full[i], 4); }
+    tc::mbar_init(&ss->tmem_full[0], 1);
+    tc::mbar_init(&ss->xchg_full[0], 4);
     tc::fence_barrier_init();
   }
   if (!kBwd && threadIdx.x >= 64 && threadIdx.x < 128) ss->bias[threadIdx.x - 64] = p.bias[nb * BN + threadIdx.x - 64];
-  if (warp == 2) { tc::tmem_alloc(&ss->tmem_slot, kTmemCols); tc::tmem_relinquish(); }
+  if (warp == 2) { tc::tmem_alloc(&ss->tmem_slot, 64); tc::tmem_relinquish(); }
   tc::fence_before_sync();
   __syncthreads();
   if (kBwd) cluster_sync_all();                 // peers' mbarriers are initialised before anyone arrives remotely
   tc::fence_after_sync();
   const uint32_t tmem_d = ss->tmem_slot;
+  const int pairs = num_kb >> 1, odd = num_kb & 1;
 
   if (warp == 0) {
-    // ======================================================================== TMA producer
-    // whole warp, uniform control flow; one elected lane issues (see tc::elect_one)
+    // ======================================================================== producer
     const uint32_t w_bar = tc::smem_u32(&ss->w_full);
     if (tc::elect_one()) {
       tc::mbar_expect_tx_u32(w_bar, (uint32_t)(num_kb * kWBlockBytes));
@@ -228,177 +226,218 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int nkb_all = (kBwd ? 4 : 1) * num_kb;
     uint32_t stage = 0, phase = 0;
     bool ok = true;
-    for (int s = kBwd ? 1 : 0; s < steps && ok; ++s) {
-      const int tsl = kBwd ? p.T - s : s;       // forward step s consumes h_seq[s]; backward iteration s consumes dG[T-s]
-      for (int tile = 0; tile < kTiles && ok; ++tile) {
-        const int mb = g * kTiles + tile;
-        if (s > 0) ok = wait_counter(p.sync + mb, (unsigned)s * p.tiles_n, abort_flag);
-        asm volatile("fence.proxy.async.global;" ::: "memory");
-        if (p.dbg && blockIdx.x == 0 && tile == 0 && lane == 0) p.dbg[4 * s + 0] = gtime();
-        // contiguous 16 KB blocks = the 128B-swizzled K-major [128 x 64] tile images written by the epilogues
-        const __nv_bfloat16* src = p.a_tiled + (((size_t)tsl * p.tiles_m + mb) * nkb_all + (kBwd ? ks * num_kb : 0)) * (BM * BK);
-        for (int kb = 0; kb < num_kb; ++kb, src += BM * BK) {
-          if (!tc::mbar_try_wait_u32(empty0 + 8 * stage, phase ^ 1)) {
-            ok = wait_bar<false>(&ss->empty[stage], phase ^ 1, abort_flag);
-            if (!ok) break;
-          }
-          if (tc::elect_one()) {
-            const uint32_t fb = full0 + 8 * stage;
-            if (p.debug_mode == 1) {
-              tc::mbar_arrive(&ss->full[stage]);
-            } else {
-              tc::mbar_expect_tx_u32(fb, kABytes);
-              tc::bulk_load_1d_u32(a0 + stage * kABytes, src, kABytes, fb);
-            }
-          }
-          __syncwarp();
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+    // one k-block: the operand is a contiguous 16 KB block = the 128B-swizzled K-major [128 x 64] tile image written by
+    // the epilogues (no tensor map, no coordinates)
+    auto load_block = [&](const __nv_bfloat16* src) -> bool {
+      if (!tc::mbar_try_wait_u32(empty0 + 8 * stage, phase ^ 1)) {
+        if (!wait_bar<false>(&ss->empty[stage], phase ^ 1, abort_flag)) return false;
+      }
+      if (tc::elect_one()) {
+        const uint32_t fb = full0 + 8 * stage;
+        if (p.debug_mode == 1) tc::mbar_arrive(&ss->full[stage]);
+        else { tc::mbar_expect_tx_u32(fb, kABytes); tc::bulk_load_1d_u32(a0 + stage * kABytes, src, kABytes, fb); }
+      }
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+      return true;
+    };
+    // two k-blocks per turn (both empty-barrier try_waits in flight together, two copies issued back to back)
+    auto load_pair = [&](const __nv_bfloat16* src) -> bool {
+      uint32_t s1 = stage + 1, ph1 = phase;
+      if (s1 == kStages) { s1 = 0; ph1 ^= 1; }
+      const bool r0 = tc::mbar_try_wait_u32(empty0 + 8 * stage, phase ^ 1);
+      const bool r1 = tc::mbar_try_wait_u32(empty0 + 8 * s1, ph1 ^ 1);
+      if (!r0 && !wait_bar<false>(&ss->empty[stage], phase ^ 1, abort_flag)) return false;
+      if (!r1 && !wait_bar<false>(&ss->empty[s1], ph1 ^ 1, abort_flag)) return false;
+      if (tc::elect_one()) {
+        const uint32_t fb0 = full0 + 8 * stage, fb1 = full0 + 8 * s1;
+        if (p.debug_mode == 1) { tc::mbar_arrive(&ss->full[stage]); tc::mbar_arrive(&ss->full[s1]); }
+        else {
+          tc::mbar_expect_tx_u32(fb0, kABytes);
+          tc::bulk_load_1d_u32(a0 + stage * kABytes, src, kABytes, fb0);
+          tc::mbar_expect_tx_u32(fb1, kABytes);
+          tc::bulk_load_1d_u32(a0 + s1 * kABytes, src + BM * BK, kABytes, fb1);
         }
       }
+      __syncwarp();
+      stage = s1 + 1; phase = ph1;
+      if (stage == kStages) { stage = 0; phase ^= 1; }
+      return true;
+    };
+    for (int s = kBwd ? 1 : 0; s < steps && ok; ++s) {
+      const int tsl = kBwd ? p.T - s : s;       // forward step s consumes h_seq[s]; backward iteration s consumes dG[T-s]
+      if (s > 0) ok = wait_counter(counter, (unsigned)s * p.tiles_n, abort_flag);
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[4 * s + 0] = gtime();
+      const __nv_bfloat16* src = p.a_tiled + (((size_t)tsl * p.tiles_m + mb) * nkb_all + (kBwd ? ks * num_kb : 0)) * (BM * BK);
+      for (int pr = 0; pr < pairs && ok; ++pr, src += 2 * BM * BK) ok = load_pair(src);
+      if (odd && ok) ok = load_block(src);
     }
   } else if (warp == 1) {
     // ======================================================================== MMA issuer
-    // whole warp, uniform control flow; one elected lane issues tcgen05.mma / tcgen05.commit
     constexpr uint32_t idesc = tc::make_idesc_bf16_f32(BM, BN);
     bool ok = wait_bar<false>(&ss->w_full, 0, abort_flag);
     const uint32_t full0 = tc::smem_u32(&ss->full[0]), empty0 = tc::smem_u32(&ss->empty[0]);
-    const uint32_t tfull0 = tc::smem_u32(&ss->tmem_full[0]);
+    const uint32_t tfull = tc::smem_u32(&ss->tmem_full[0]);
     const uint64_t desc_a0 = tc::desc_kmajor_sw128(tc::smem_u32(smem_a));      // + stage * (kABytes >> 4)
     const uint64_t desc_w0 = tc::desc_kmajor_sw128(tc::smem_u32(smem_w));      // + kb * (kWBlockBytes >> 4)
     uint32_t stage = 0, phase = 0;
+    const bool prof = p.dbg && blockIdx.x == 0;
+    constexpr int kGroup = kStages >= 5 ? 4 : 2;              // k-blocks per turn: all their try_waits are in flight together
     for (int s = kBwd ? 1 : 0; s < steps && ok; ++s) {
-      for (int tile = 0; tile < kTiles && ok; ++tile) {
-        const uint32_t acc = tmem_d + tile * BN;
-        uint64_t db = desc_w0;
-        for (int kb = 0; kb < num_kb; ++kb, db += (kWBlockBytes >> 4)) {
-          if (!tc::mbar_try_wait_u32(full0 + 8 * stage, phase)) {
-            ok = wait_bar<false>(&ss->full[stage], phase, abort_flag);
-            if (!ok) break;
+      uint64_t db = desc_w0;
+      long long t_wait = 0, t_begin = prof ? clock64() : 0, t_first = 0;
+      for (int kb = 0; kb < num_kb && ok; kb += kGroup) {
+        const int g = (num_kb - kb) < kGroup ? (num_kb - kb) : kGroup;
+        uint32_t st[kGroup], ph[kGroup];
+        bool rdy[kGroup];
+        {
+          uint32_t sx = stage, px = phase;
+#pragma unroll
+          for (int i = 0; i < kGroup; ++i) {
+            st[i] = sx; ph[i] = px;
+            if (++sx == kStages) { sx = 0; px ^= 1; }
           }
-          tc::fence_after_sync();
-          if (tc::elect_one()) {
-            if (p.debug_mode == 2) {
-              tc::mbar_arrive(&ss->empty[stage]);
-              if (kb == num_kb - 1) tc::mbar_arrive(&ss->tmem_full[tile]);
-            } else {
-              const uint64_t da = desc_a0 + (uint64_t)(stage * (kABytes >> 4));
-              if (kb == 0) tc::mma_bf16_ss_first(acc, da, db, idesc); else tc::mma_bf16_ss_acc(acc, da, db, idesc);
-              tc::mma_bf16_ss_acc(acc, da + 2, db + 2, idesc);
-              tc::mma_bf16_ss_acc(acc, da + 4, db + 4, idesc);
-              tc::mma_bf16_ss_acc(acc, da + 6, db + 6, idesc);
-              tc::mma_commit_u32(empty0 + 8 * stage);
-              if (kb == num_kb - 1) tc::mma_commit_u32(tfull0 + 8 * tile);
+        }
+        const long long tw0 = prof ? clock64() : 0;
+#pragma unroll
+        for (int i = 0; i < kGroup; ++i) rdy[i] = (i < g) ? tc::mbar_try_wait_u32(full0 + 8 * st[i], ph[i]) : true;
+#pragma unroll
+        for (int i = 0; i < kGroup; ++i)
+          if (ok && !rdy[i]) ok = wait_bar<false>(&ss->full[st[i]], ph[i], abort_flag);
+        if (!ok) break;
+        if (prof) { const long long tw1 = clock64(); if (kb == 0) t_first = tw1 - tw0; else t_wait += tw1 - tw0; }
+        tc::fence_after_sync();
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int i = 0; i < kGroup; ++i) {
+            if (i < g) {
+              if (p.debug_mode == 2) {
+                tc::mbar_arrive(&ss->empty[st[i]]);
+              } else {
+                const uint64_t da = desc_a0 + (uint64_t)(st[i] * (kABytes >> 4));
+                const uint64_t dbi = db + (uint64_t)(i * (kWBlockBytes >> 4));
+                if (kb == 0 && i == 0) tc::mma_bf16_ss_first(tmem_d, da, dbi, idesc); else tc::mma_bf16_ss_acc(tmem_d, da, dbi, idesc);
+                tc::mma_bf16_ss_acc(tmem_d, da + 2, dbi + 2, idesc);
+                tc::mma_bf16_ss_acc(tmem_d, da + 4, dbi + 4, idesc);
+                tc::mma_bf16_ss_acc(tmem_d, da + 6, dbi + 6, idesc);
+                tc::mma_commit_u32(empty0 + 8 * st[i]);
+              }
             }
           }
-          __syncwarp();
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (kb + g >= num_kb) { if (p.debug_mode == 2) tc::mbar_arrive(&ss->tmem_full[0]); else tc::mma_commit_u32(tfull); }
         }
+        __syncwarp();
+        db += (uint64_t)(g * (kWBlockBytes >> 4));
+#pragma unroll
+        for (int i = 0; i < kGroup; ++i)
+          if (i < g) { if (++stage == kStages) { stage = 0; phase ^= 1; } }
+      }
+      if (prof && lane == 0) {           // [first-turn wait (incl. grid barrier + first loads), later waits, whole step] in cycles
+        p.dbg[4 * s + 3] = (unsigned long long)t_first | ((unsigned long long)t_wait << 20) | ((unsigned long long)(clock64() - t_begin) << 40);
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ======================================================================== epilogue (one 4-warp group per batch tile)
+    // ======================================================================== epilogue (8 warps)
     const int ewi = warp - kEpiWarp0;
-    const int quarter = ewi & 3, tile = ewi >> 2;
+    const int quarter = ewi & 3, half = ewi >> 2;
     const int rloc = quarter * 32 + lane;
-    const int mb = g * kTiles + tile;
+    const int etid = ewi * 32 + lane;
     const int row = mb * BM + rloc;
     const bool valid = row < p.B;
     const int H = p.H, B = p.B;
-    const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + tile * BN;
-    unsigned int* counter = p.sync + mb;
-    uint64_t* tfull = &ss->tmem_full[tile];
+    const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + 32 * half;
+    uint64_t* tfull = &ss->tmem_full[0];
     uint32_t tphase = 0;
     bool ok = true;
-    const bool dbg_thread = p.dbg && blockIdx.x == 0 && ewi == 0 && lane == 0;
-    auto group_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + tile) : "memory"); };
+    const bool dbg_thread = p.dbg && blockIdx.x == 0 && etid == 0;
+    auto epi_bar = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    // grid-barrier arrive: the CTA barrier orders every epilogue thread's writes before this thread's fence + release
+    // (same pattern as cooperative-groups grid sync), the proxy fence covers the async-proxy (bulk copy) readers
+    auto signal = [&]() {
+      // ONE gpu-scope release (each fence is a full L2 round trip, ~0.8 us: three of them used to dominate the
+      // epilogue); the generic->async proxy fence is on the consumer side, after its acquire
+      signal_counter(counter);
+    };
 
     if (!kBwd) {
-      const int j0 = nb * 16;
-      const int n0 = nb * 64;
+      const int j0 = nb * 16 + 8 * half;            // this thread's 8 hidden units
+      const int n0 = nb * 64 + 32 * half;           // = its 32 gate columns
+      const float* bs = ss->bias + 32 * half;
       for (int t = 0; t < p.T && ok; ++t) {
         // operands that do not depend on the GEMM: issue their loads before waiting on the accumulator
-        uint4 gxv[8];
-        float4 cv[4];
+        uint4 gxv[4];
+        float4 cv[2];
         if (valid) {
           const __nv_bfloat16* gp = p.gx + ((size_t)t * B + row) * (4 * H) + n0;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) gxv[i] = ldg_nc16(gp + 8 * i);
+          for (int i = 0; i < 4; ++i) gxv[i] = ldg_nc16(gp + 8 * i);
           const float* cp = p.c_seq + ((size_t)t * B + row) * H + j0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) cv[i] = *reinterpret_cast<const float4*>(cp + 4 * i);
+          cv[0] = *reinterpret_cast<const float4*>(cp); cv[1] = *reinterpret_cast<const float4*>(cp + 4);
+          if (t + 2 < p.T) prefetch_l2(gp + (size_t)2 * B * (4 * H));       // the x-projection comes from HBM: pull it into L2 early
         }
         ok = wait_bar<false>(tfull, tphase, abort_flag);
         tphase ^= 1;
         if (!ok) break;
         tc::fence_after_sync();
         if (dbg_thread) p.dbg[4 * t + 1] = gtime();
-        float cn[16];
-        uint32_t hpk[8];
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {           // 32 accumulator columns (8 hidden units) per pass
-          uint32_t v[32];
-          tc::tmem_ld32(taddr + 32 * pass, v);
-          tc::tmem_ld_wait();
-          uint32_t apk[16];
-          const float* bs = ss->bias + 32 * pass;
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const uint4 g4 = gxv[4 * pass + (jj >> 1)];
-            const uint32_t ga = (jj & 1) ? g4.z : g4.x, gb = (jj & 1) ? g4.w : g4.y;
-            const float pi = __uint_as_float(v[4 * jj + 0]) + bf_lo(ga) + bs[4 * jj + 0];
-            const float pf = __uint_as_float(v[4 * jj + 1]) + bf_hi(ga) + bs[4 * jj + 1];
-            const float pg = __uint_as_float(v[4 * jj + 2]) + bf_lo(gb) + bs[4 * jj + 2];
-            const float po = __uint_as_float(v[4 * jj + 3]) + bf_hi(gb) + bs[4 * jj + 3];
-            const float ig = ts::sigmoidf_fast(pi), fg = ts::sigmoidf_fast(pf), gg = ts::tanhf_fast(pg), og = ts::sigmoidf_fast(po);
-            const float c = fg * reinterpret_cast<const float*>(cv)[8 * pass + jj] + ig * gg;
-            cn[8 * pass + jj] = c;
-            const float h = og * ts::tanhf_fast(c);
-            if (jj & 1) hpk[4 * pass + (jj >> 1)] = pack_bf2(__uint_as_float(hpk[4 * pass + (jj >> 1)]), h);
-            else hpk[4 * pass + (jj >> 1)] = __float_as_uint(h);
-            apk[2 * jj] = pack_bf2(ig, fg);
-            apk[2 * jj + 1] = pack_bf2(gg, og);
-          }
-          {
-            // next step's operand: the same 8 values into the swizzled tile image (16 B chunk c of row r sits at c ^ (r & 7))
-            const size_t blk = ((size_t)(t + 1) * p.tiles_m + mb) * (H / BK) + (j0 / BK);
-            const int chunk = ((j0 % BK) / 8 + pass) ^ (rloc & 7);
-            stg16(p.a_tiled + blk * (BM * BK) + rloc * BK + chunk * 8,
-                  make_uint4(hpk[4 * pass], hpk[4 * pass + 1], hpk[4 * pass + 2], hpk[4 * pass + 3]));
-          }
-          if (valid) {
-            // h first: it is the only thing other CTAs wait for (act is private to this thread's next backward)
-            const uint4 h8 = make_uint4(hpk[4 * pass], hpk[4 * pass + 1], hpk[4 * pass + 2], hpk[4 * pass + 3]);
-            stg16(p.h_seq + ((size_t)(t + 1) * B + row) * H + j0 + 8 * pass, h8);
-            __nv_bfloat16* ap = p.act + ((size_t)t * B + row) * (4 * H) + n0 + 32 * pass;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) stg16(ap + 8 * i, make_uint4(apk[4 * i], apk[4 * i + 1], apk[4 * i + 2], apk[4 * i + 3]));
-          }
-        }
+        uint32_t v[32];
+        tc::tmem_ld32(taddr, v);
+        tc::tmem_ld_wait();
         tc::fence_before_sync();
-        __threadfence();
-        asm volatile("fence.proxy.async.global;" ::: "memory");     // these rows are read next by TMA (async proxy)
-        group_bar();
-        if (rloc == 0) {
-          signal_counter(counter);
+        if (dbg_thread && t == 8) p.dbg[4 * (p.T + 2) + 0] = gtime();
+        float cn[8], hv[8];
+        uint32_t apk[16];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const uint4 g4 = gxv[jj >> 1];
+          const uint32_t ga = (jj & 1) ? g4.z : g4.x, gb = (jj & 1) ? g4.w : g4.y;
+          const float pi = __uint_as_float(v[4 * jj + 0]) + bf_lo(ga) + bs[4 * jj + 0];
+          const float pf = __uint_as_float(v[4 * jj + 1]) + bf_hi(ga) + bs[4 * jj + 1];
+          const float pg = __uint_as_float(v[4 * jj + 2]) + bf_lo(gb) + bs[4 * jj + 2];
+          const float po = __uint_as_float(v[4 * jj + 3]) + bf_hi(gb) + bs[4 * jj + 3];
+          const float ig = ts::sigmoidf_fast(pi), fg = ts::sigmoidf_fast(pf), gg = ts::tanhf_fast(pg), og = ts::sigmoidf_fast(po);
+          const float c = fg * reinterpret_cast<const float*>(cv)[jj] + ig * gg;
+          cn[jj] = c;
+          hv[jj] = og * ts::tanhf_fast(c);
+          apk[2 * jj] = pack_bf2(ig, fg);
+          apk[2 * jj + 1] = pack_bf2(gg, og);
+        }
+        const uint4 h8 = make_uint4(pack_bf2(hv[0], hv[1]), pack_bf2(hv[2], hv[3]), pack_bf2(hv[4], hv[5]), pack_bf2(hv[6], hv[7]));
+        {
+          // next step's operand first (the only thing other CTAs wait for): 8 values = one 16 B chunk of the swizzled
+          // tile image; chunk c of row r sits at position c ^ (r & 7)
+          const size_t blk = ((size_t)(t + 1) * p.tiles_m + mb) * (H / BK) + (j0 / BK);
+          const int chunk = ((j0 % BK) / 8) ^ (rloc & 7);
+          stg16(p.a_tiled + blk * (BM * BK) + rloc * BK + chunk * 8, h8);
+        }
+        if (dbg_thread && t == 8) p.dbg[4 * (p.T + 2) + 1] = gtime();
+        epi_bar();
+        if (etid == 0) {
+          if (dbg_thread && t == 8) p.dbg[4 * (p.T + 2) + 2] = gtime();
+          signal();
           if (dbg_thread) p.dbg[4 * t + 2] = gtime();
         }
-        if (valid) {
+        if (valid) {                                   // everything below is off the critical path
+          stg16(p.h_seq + ((size_t)(t + 1) * B + row) * H + j0, h8);
           float* cp = p.c_seq + ((size_t)(t + 1) * B + row) * H + j0;
+          *reinterpret_cast<float4*>(cp) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+          *reinterpret_cast<float4*>(cp + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+          __nv_bfloat16* ap = p.act + ((size_t)t * B + row) * (4 * H) + n0;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(cp + 4 * i) = make_float4(cn[4 * i], cn[4 * i + 1], cn[4 * i + 2], cn[4 * i + 3]);
+          for (int i = 0; i < 4; ++i) stg16(ap + 8 * i, make_uint4(apk[4 * i], apk[4 * i + 1], apk[4 * i + 2], apk[4 * i + 3]));
         }
       }
     } else {
-      // after the reduce-scatter this cluster member owns hidden [64 nb + 16 ks, +16) of this batch tile
-      const int j0 = nb * 64 + ks * 16;
-      uint8_t* xbuf = smem_x + tile * kXchgBytes;                 // [4 src][128 rows][16 bf16]
-      const uint32_t xbase = tc::smem_u32(xbuf);
-      const uint32_t xbar = tc::smem_u32(&ss->xchg_full[tile]);
+      // after the reduce-scatter this cluster member owns hidden [64 nb + 16 ks, +16); this thread 8 of them
+      const int j0 = nb * 64 + ks * 16 + 8 * half;
+      const uint32_t xbase = tc::smem_u32(smem_x);                // [4 src][128 rows][16 bf16]
+      const uint32_t xbar = tc::smem_u32(&ss->xchg_full[0]);
       uint32_t xphase = 0;
-      float dc[16], dh[16];
+      float dc[8], dh[8];
       if (valid) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 2; ++i) {
           float4 a = *reinterpret_cast<const float4*>(p.dc0 + (size_t)row * H + j0 + 4 * i);
           float4 b = *reinterpret_cast<const float4*>(p.dh0 + (size_t)row * H + j0 + 4 * i);
           dc[4 * i] = a.x; dc[4 * i + 1] = a.y; dc[4 * i + 2] = a.z; dc[4 * i + 3] = a.w;
@@ -406,21 +445,26 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { dc[i] = 0.f; dh[i] = 0.f; }
+        for (int i = 0; i < 8; ++i) { dc[i] = 0.f; dh[i] = 0.f; }
       }
       for (int s = 0; s <= p.T && ok; ++s) {
         const int t = p.T - 1 - s;
-        uint4 av[8], dhv[2];
+        uint4 av[4], dhv;
+        float4 cpv[2], cnv[2];
         if (valid && s < p.T) {
           const __nv_bfloat16* ap = p.act + ((size_t)t * B + row) * (4 * H) + 4 * j0;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) av[i] = ldg_nc16(ap + 8 * i);
-          const __nv_bfloat16* dp = p.dh_seq + ((size_t)t * B + row) * H + j0;
-          dhv[0] = ldg_nc16(dp); dhv[1] = ldg_nc16(dp + 8);
-          // the cell states come from HBM (saved by the forward pass): pull their lines into L2 now, they are
-          // consumed after the GEMM + exchange
-          prefetch_l2(p.c_seq + ((size_t)t * B + row) * H + j0);
-          prefetch_l2(p.c_seq + ((size_t)(t + 1) * B + row) * H + j0);
+          for (int i = 0; i < 4; ++i) av[i] = ldg_nc16(ap + 8 * i);
+          dhv = ldg_nc16(p.dh_seq + ((size_t)t * B + row) * H + j0);
+          const float* c0p = p.c_seq + ((size_t)t * B + row) * H + j0;
+          const float* c1p = p.c_seq + ((size_t)(t + 1) * B + row) * H + j0;
+          cpv[0] = *reinterpret_cast<const float4*>(c0p); cpv[1] = *reinterpret_cast<const float4*>(c0p + 4);
+          cnv[0] = *reinterpret_cast<const float4*>(c1p); cnv[1] = *reinterpret_cast<const float4*>(c1p + 4);
+          if (t >= 2) {                                                        // saved activations come from HBM: pull t-2 into L2 early
+            prefetch_l2(ap - (size_t)2 * B * (4 * H));
+            prefetch_l2(c0p - (size_t)2 * B * H);
+            prefetch_l2(p.dh_seq + ((size_t)(t - 2) * B + row) * H + j0);
+          }
         }
         if (s > 0) {
           ok = wait_bar<false>(tfull, tphase, abort_flag);
@@ -428,92 +472,78 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           if (!ok) break;
           tc::fence_after_sync();
           if (dbg_thread) p.dbg[4 * s + 1] = gtime();
+          uint32_t v[32];
+          tc::tmem_ld32(taddr, v);
+          tc::tmem_ld_wait();
+          tc::fence_before_sync();
           // reduce-scatter over the 4 K-quarters: column chunk q (16 wide, bf16) goes to member q's slot [ks] (DSMEM)
 #pragma unroll
-          for (int pass = 0; pass < 2; ++pass) {
-            uint32_t v[32];
-            tc::tmem_ld32(taddr + 32 * pass, v);
-            tc::tmem_ld_wait();
+          for (int qq = 0; qq < 2; ++qq) {
+            const uint32_t dst = mapa(xbase + (uint32_t)((ks * BM + rloc) * 32), (uint32_t)(2 * half + qq));
+            uint32_t pk[8];
 #pragma unroll
-            for (int qq = 0; qq < 2; ++qq) {
-              const uint32_t dst = mapa(xbase + (uint32_t)((ks * BM + rloc) * 32), (uint32_t)(2 * pass + qq));
-              uint32_t pk[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) pk[i] = pack_bf2(__uint_as_float(v[16 * qq + 2 * i]), __uint_as_float(v[16 * qq + 2 * i + 1]));
-              st_cluster_u4(dst, make_uint4(pk[0], pk[1], pk[2], pk[3]));
-              st_cluster_u4(dst + 16, make_uint4(pk[4], pk[5], pk[6], pk[7]));
-            }
+            for (int i = 0; i < 8; ++i) pk[i] = pack_bf2(__uint_as_float(v[16 * qq + 2 * i]), __uint_as_float(v[16 * qq + 2 * i + 1]));
+            st_cluster_u4(dst, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+            st_cluster_u4(dst + 16, make_uint4(pk[4], pk[5], pk[6], pk[7]));
           }
-          tc::fence_before_sync();
-          group_bar();
-          if (rloc < 4) mbar_arrive_remote(mapa(xbar, (uint32_t)rloc));
-          ok = wait_bar<true>(&ss->xchg_full[tile], xphase, abort_flag);
+          epi_bar();
+          if (etid < 4) mbar_arrive_remote(mapa(xbar, (uint32_t)etid));
+          ok = wait_bar<true>(&ss->xchg_full[0], xphase, abort_flag);
           xphase ^= 1;
           if (!ok) break;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) dh[i] = 0.f;
+          for (int i = 0; i < 8; ++i) dh[i] = 0.f;
 #pragma unroll
           for (int src = 0; src < 4; ++src) {
-            const uint4* xp = reinterpret_cast<const uint4*>(xbuf + (size_t)(src * BM + rloc) * 32);
-            const uint4 x0 = xp[0], x1 = xp[1];
-            const uint32_t w[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            const uint4 x4 = *reinterpret_cast<const uint4*>(smem_x + (size_t)(src * BM + rloc) * 32 + 16 * half);
+            const uint32_t w[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { dh[2 * i] += bf_lo(w[i]); dh[2 * i + 1] += bf_hi(w[i]); }
+            for (int i = 0; i < 4; ++i) { dh[2 * i] += bf_lo(w[i]); dh[2 * i + 1] += bf_hi(w[i]); }
           }
         }
         if (s == p.T) {
           if (valid) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 2; ++i) {
               *reinterpret_cast<float4*>(p.dh0 + (size_t)row * H + j0 + 4 * i) = make_float4(dh[4 * i], dh[4 * i + 1], dh[4 * i + 2], dh[4 * i + 3]);
               *reinterpret_cast<float4*>(p.dc0 + (size_t)row * H + j0 + 4 * i) = make_float4(dc[4 * i], dc[4 * i + 1], dc[4 * i + 2], dc[4 * i + 3]);
             }
           }
           break;
         }
-        if (valid) {
-          const float* c0p = p.c_seq + ((size_t)t * B + row) * H + j0;
-          const float* c1p = p.c_seq + ((size_t)(t + 1) * B + row) * H + j0;
+        uint32_t gpk[16];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const uint4 a4 = av[jj >> 1];
+          const uint32_t aa = (jj & 1) ? a4.z : a4.x, ab = (jj & 1) ? a4.w : a4.y;
+          const float ig = bf_lo(aa), fg = bf_hi(aa), gg = bf_lo(ab), og = bf_hi(ab);
+          const uint32_t dw = (jj >> 1) == 0 ? dhv.x : (jj >> 1) == 1 ? dhv.y : (jj >> 1) == 2 ? dhv.z : dhv.w;
+          const float dht = dh[jj] + ((jj & 1) ? bf_hi(dw) : bf_lo(dw));
+          const float cprev = reinterpret_cast<const float*>(cpv)[jj];
+          const float tcn = ts::tanhf_fast(reinterpret_cast<const float*>(cnv)[jj]);
+          const float dct = dc[jj] + dht * og * (1.f - tcn * tcn);
+          const float d_o = dht * tcn, d_i = dct * gg, d_f = dct * cprev, d_g = dct * ig;
+          dc[jj] = dct * fg;
+          gpk[2 * jj] = pack_bf2(d_i * ig * (1.f - ig), d_f * fg * (1.f - fg));
+          gpk[2 * jj + 1] = pack_bf2(d_g * (1.f - gg * gg), d_o * og * (1.f - og));
+        }
+        {
+          // next iteration's operand first: this thread's 32 gate columns = 4 chunks of row rloc of k-block j0/16
+          const size_t blk = ((size_t)t * p.tiles_m + mb) * (4 * H / BK) + (j0 / 16);
+          __nv_bfloat16* tp = p.a_tiled + blk * (BM * BK) + rloc * BK;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            stg16(tp + (((4 * half + i) ^ (rloc & 7)) * 8), make_uint4(gpk[4 * i], gpk[4 * i + 1], gpk[4 * i + 2], gpk[4 * i + 3]));
+        }
+        epi_bar();
+        if (etid == 0) {
+          signal();
+          if (dbg_thread) p.dbg[4 * s + 2] = gtime();
+        }
+        if (valid) {                                   // the [T,B,4H] copy for the weight-gradient GEMMs: off the critical path
           __nv_bfloat16* gp = p.dpre + ((size_t)t * B + row) * (4 * H) + 4 * j0;
 #pragma unroll
-          for (int pass = 0; pass < 2; ++pass) {
-            float4 cpv[2], cnv[2];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) { cpv[i] = *reinterpret_cast<const float4*>(c0p + 8 * pass + 4 * i); cnv[i] = *reinterpret_cast<const float4*>(c1p + 8 * pass + 4 * i); }
-            uint32_t gpk[16];
-#pragma unroll
-            for (int j8 = 0; j8 < 8; ++j8) {
-              const int jj = 8 * pass + j8;
-              const uint4 a4 = av[jj >> 1];
-              const uint32_t aa = (jj & 1) ? a4.z : a4.x, ab = (jj & 1) ? a4.w : a4.y;
-              const float ig = bf_lo(aa), fg = bf_hi(aa), gg = bf_lo(ab), og = bf_hi(ab);
-              const uint4 d4 = dhv[pass];
-              const uint32_t dw = (j8 >> 1) == 0 ? d4.x : (j8 >> 1) == 1 ? d4.y : (j8 >> 1) == 2 ? d4.z : d4.w;
-              const float dht = dh[jj] + ((jj & 1) ? bf_hi(dw) : bf_lo(dw));
-              const float cprev = reinterpret_cast<const float*>(cpv)[j8];
-              const float tcn = ts::tanhf_fast(reinterpret_cast<const float*>(cnv)[j8]);
-              const float dct = dc[jj] + dht * og * (1.f - tcn * tcn);
-              const float d_o = dht * tcn, d_i = dct * gg, d_f = dct * cprev, d_g = dct * ig;
-              dc[jj] = dct * fg;
-              gpk[2 * j8] = pack_bf2(d_i * ig * (1.f - ig), d_f * fg * (1.f - fg));
-              gpk[2 * j8 + 1] = pack_bf2(d_g * (1.f - gg * gg), d_o * og * (1.f - og));
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) stg16(gp + 32 * pass + 8 * i, make_uint4(gpk[4 * i], gpk[4 * i + 1], gpk[4 * i + 2], gpk[4 * i + 3]));
-            // next iteration's operand: this thread's 64 gate columns are exactly row rloc of k-block j0/16
-            const size_t blk = ((size_t)t * p.tiles_m + mb) * (4 * H / BK) + (j0 / 16);
-            __nv_bfloat16* tp = p.a_tiled + blk * (BM * BK) + rloc * BK;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              stg16(tp + (((4 * pass + i) ^ (rloc & 7)) * 8), make_uint4(gpk[4 * i], gpk[4 * i + 1], gpk[4 * i + 2], gpk[4 * i + 3]));
-          }
-        }
-        __threadfence();
-        asm volatile("fence.proxy.async.global;" ::: "memory");
-        group_bar();
-        if (rloc == 0) {
-          signal_counter(counter);
-          if (dbg_thread) p.dbg[4 * s + 2] = gtime();
+          for (int i = 0; i < 4; ++i) stg16(gp + 8 * i, make_uint4(gpk[4 * i], gpk[4 * i + 1], gpk[4 * i + 2], gpk[4 * i + 3]));
         }
       }
     }
@@ -523,22 +553,45 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   __syncthreads();
   if (kBwd) cluster_sync_all();                  // nobody exits while a peer may still write into / arrive on its smem
   if (threadIdx.x == 0 && ss->abort_flag) atomicExch(reinterpret_cast<int*>(p.sync + 63), 1);
-  if (warp == 2) tc::tmem_dealloc(tmem_d, kTmemCols);
+  if (warp == 2) tc::tmem_dealloc(tmem_d, 64);
 }
 
-size_t smem_bytes(int H, bool bwd, int stages, int tiles) {
-  return (size_t)(H / BK) * kWBlockBytes + (size_t)stages * kABytes + (bwd ? tiles * kXchgBytes : 0) + sizeof(SeqSmem) + 1024;
+// One small launch instead of ~12 framework ops: h_seq[0] <- h0, c_seq[0] <- c0, the swizzled tile image of h0 (slot 0
+// of the streamed operand, zero rows beyond B), and the step counters <- 0.
+__global__ void seq_prologue_kernel(const __nv_bfloat16* __restrict__ h0, const float* __restrict__ c0,
+                                    __nv_bfloat16* __restrict__ h_seq0, float* __restrict__ c_seq0,
+                                    __nv_bfloat16* __restrict__ tiled0, unsigned int* __restrict__ sync, int B, int H, int tiles_m) {
+  const int nchunk = H / 8, nkb = H / BK;
+  const int total = tiles_m * BM * nchunk;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / nchunk, c = i % nchunk;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r < B) {
+      v = *reinterpret_cast<const uint4*>(h0 + (size_t)r * H + 8 * c);
+      *reinterpret_cast<uint4*>(h_seq0 + (size_t)r * H + 8 * c) = v;
+    }
+    const int mb = r / BM, rloc = r % BM, kb = c / 8, pos = (c % 8) ^ (rloc & 7);
+    *reinterpret_cast<uint4*>(tiled0 + (((size_t)mb * nkb + kb) * BM + rloc) * BK + pos * 8) = v;
+  }
+  const int n4 = B * H / 4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x)
+    reinterpret_cast<float4*>(c_seq0)[i] = reinterpret_cast<const float4*>(c0)[i];
+  if (blockIdx.x == 0 && threadIdx.x < 16) sync[threadIdx.x] = 0u;
 }
 
-template <bool kBwd, int kTiles, int kStages>
-int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tw, const SeqParams& p, int grid, cudaStream_t st) {
-  auto kern = lstm_seq_kernel<kBwd, kTiles, kStages>;
-  const size_t smem = smem_bytes(p.H, kBwd, kStages, kTiles);
+size_t smem_bytes(int H, bool bwd, int stages) {
+  return (size_t)(H / BK) * kWBlockBytes + (size_t)stages * kABytes + (bwd ? kXchgBytes : 0) + sizeof(SeqSmem) + 1024;
+}
+
+template <bool kBwd, int kStages>
+int launch_cfg(const CUtensorMap& tw, const SeqParams& p, int grid, cudaStream_t st) {
+  auto kern = lstm_seq_kernel<kBwd, kStages>;
+  const size_t smem = smem_bytes(p.H, kBwd, kStages);
   if (smem > 227 * 1024) return -4;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128 + 128 * kTiles); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = kBwd ? 4 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -549,80 +602,81 @@ int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tw, const SeqParams& p,
     if (e != cudaSuccess) { cudaGetLastError(); return -20; }
     if (nclusters * 4 < grid) return -21;              // not co-resident
   }
-  e = cudaLaunchKernelEx(&cfg, kern, ta, tw, p);
+  e = cudaLaunchKernelEx(&cfg, kern, tw, p);
   return (int)e;
 }
 
 template <bool kBwd>
-int dispatch(const CUtensorMap& ta, const CUtensorMap& tw, const SeqParams& p, int grid, int tiles, int stages, cudaStream_t st) {
-  if (tiles == 2) {
-    if (stages == 3) return launch_cfg<kBwd, 2, 3>(ta, tw, p, grid, st);
-    if (stages == 4) return launch_cfg<kBwd, 2, 4>(ta, tw, p, grid, st);
-    if (stages == 5) return launch_cfg<kBwd, 2, 5>(ta, tw, p, grid, st);
-    if (stages == 6) return launch_cfg<kBwd, 2, 6>(ta, tw, p, grid, st);
-  } else {
-    if (stages == 3) return launch_cfg<kBwd, 1, 3>(ta, tw, p, grid, st);
-    if (stages == 4) return launch_cfg<kBwd, 1, 4>(ta, tw, p, grid, st);
-    if (stages == 5) return launch_cfg<kBwd, 1, 5>(ta, tw, p, grid, st);
-    if (stages == 6) return launch_cfg<kBwd, 1, 6>(ta, tw, p, grid, st);
+int dispatch(const CUtensorMap& tw, const SeqParams& p, int grid, int stages, cudaStream_t st) {
+  switch (stages) {
+    case 2: return launch_cfg<kBwd, 2>(tw, p, grid, st);
+    case 3: return launch_cfg<kBwd, 3>(tw, p, grid, st);
+    case 4: return launch_cfg<kBwd, 4>(tw, p, grid, st);
+    case 5: return launch_cfg<kBwd, 5>(tw, p, grid, st);
+    case 6: return launch_cfg<kBwd, 6>(tw, p, grid, st);
   }
   return -5;
 }
 
-int pick_stages(int H, bool bwd, int tiles) {
-  for (int s = 6; s >= 3; --s)
-    if (smem_bytes(H, bwd, s, tiles) <= 227 * 1024) return s;
+int pick_stages(int H, bool bwd) {
+  for (int s = 6; s >= 2; --s)
+    if (smem_bytes(H, bwd, s) <= 227 * 1024) return s;
   return 0;
 }
 
 }  // namespace
 
 // sync_ws: >= 64 u32; [0..tiles_m) step counters (zeroed by the caller before every launch), [63] sticky error flag.
-// variant (tuning knob, 0 = defaults) = tiles_per_cta + 16*stages:  tiles_per_cta 0 -> 2 when the batch has an even
-// number of 128-row tiles, else 1;  stages 0 -> deepest ring that fits next to the resident weight slice.
+// variant (tuning knob, 0 = defaults) = 16*stages + 4096*debug_mode:  stages 0 -> deepest ring that fits next to the
+// resident weight slice.
 template <bool kBwd>
-static int seq_common(SeqParams& p, const void* a_base, uint64_t a_t, const void* w_base, int variant, cudaStream_t st) {
-  (void)a_base; (void)a_t;
+static int seq_common(SeqParams& p, const void* w_base, int variant, cudaStream_t st) {
   const int H = p.H, B = p.B;
   if (H % 64 != 0) { ts::set_last_error("lstm_seq: H must be a multiple of 64"); return -2; }
   const int tiles_m = (B + BM - 1) / BM, tiles_n = kBwd ? (H / BN) * 4 : 4 * H / BN;
-  int tiles = variant & 15, stages = (variant >> 4) & 15;
+  int stages = (variant >> 4) & 15;
   p.debug_mode = (variant >> 12) & 3;
-  if (tiles == 0) tiles = 1;
-  if (tiles == 2 && tiles_m % 2 != 0) tiles = 1;
   int dev = 0;
   cudaGetDevice(&dev);
-  const int grid = (tiles_m / tiles) * tiles_n;
+  const int grid = tiles_m * tiles_n;
   if (grid > ts::sm_count(dev)) { ts::set_last_error("lstm_seq: grid exceeds SM count (not co-resident)"); return -3; }
-  if (stages == 0) stages = pick_stages(H, kBwd, tiles);
-  if (stages == 0 || smem_bytes(H, kBwd, stages, tiles) > 227 * 1024) { ts::set_last_error("lstm_seq: weight slice does not fit in shared memory"); return -4; }
+  if (stages == 0) stages = pick_stages(H, kBwd);
+  if (stages < 2 || smem_bytes(H, kBwd, stages) > 227 * 1024) { ts::set_last_error("lstm_seq: weight slice does not fit in shared memory"); return -4; }
   const int K = kBwd ? 4 * H : H, N = kBwd ? H : 4 * H;
-  CUtensorMap ta, tw;
+  CUtensorMap tw;
   if (int rc = ts::make_tmap_2d_bf16(&tw, w_base, (uint64_t)N, (uint64_t)K, (uint64_t)K, BK, BN)) return rc;
-  ta = tw;                                     // the streamed operand no longer goes through a tensor map
   p.tiles_n = tiles_n;
   p.tiles_m = tiles_m;
-  int rc = dispatch<kBwd>(ta, tw, p, grid, tiles, stages, st);
+  int rc = dispatch<kBwd>(tw, p, grid, stages, st);
   if (rc == -21) ts::set_last_error("lstm_seq_bwd: clusters of 4 are not co-resident on this device");
   return rc;
 }
 
 extern "C" int ts_lstm_seq_fwd(const void* gx, const void* w_h, const float* bias, const void* h_seq, const float* c_seq,
-                               void* act, float*, void* dbg, void* a_tiled, int T, int B, int H, unsigned int* sync_ws, int variant,
-                               cudaStream_t st) {
+                               void* act, const float* c0, void* dbg, void* a_tiled, int T, int B, int H, unsigned int* sync_ws, int variant,
+                               cudaStream_t st, const void* h0) {
+  {
+    const int tiles_m = (B + BM - 1) / BM;
+    const int total = tiles_m * BM * (H / 8);
+    int blocks = (total + 255) / 256;
+    if (blocks > 592) blocks = 592;
+    seq_prologue_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)h0, c0, (__nv_bfloat16*)h_seq, (float*)c_seq,
+                                                (__nv_bfloat16*)a_tiled, sync_ws, B, H, tiles_m);
+  }
   SeqParams p{};
   p.a_tiled = (__nv_bfloat16*)a_tiled;
   p.gx = (const __nv_bfloat16*)gx; p.bias = bias; p.h_seq = (__nv_bfloat16*)h_seq; p.c_seq = (float*)c_seq;
   p.act = (__nv_bfloat16*)act; p.sync = sync_ws; p.T = T; p.B = B; p.H = H; p.dbg = (unsigned long long*)dbg;
-  return seq_common<false>(p, h_seq, (uint64_t)T + 1, w_h, variant, st);
+  return seq_common<false>(p, w_h, variant, st);
 }
 
 extern "C" int ts_lstm_seq_bwd(const void* dh_seq, const void* w_hT, const void* act, const float* c_seq, const void* dpre,
                                float* dh0, float* dc0, void* dbg, void* a_tiled, int T, int B, int H, unsigned int* sync_ws, int variant,
                                cudaStream_t st) {
+  cudaMemsetAsync(sync_ws, 0, 16 * sizeof(unsigned int), st);      // step counters restart at 0 every launch
   SeqParams p{};
   p.a_tiled = (__nv_bfloat16*)a_tiled;
   p.dh_seq = (const __nv_bfloat16*)dh_seq; p.act = (__nv_bfloat16*)act; p.c_seq = (float*)c_seq; p.dpre = (__nv_bfloat16*)dpre;
   p.dh0 = dh0; p.dc0 = dc0; p.sync = sync_ws; p.T = T; p.B = B; p.H = H; p.dbg = (unsigned long long*)dbg;
-  return seq_common<true>(p, dpre, (uint64_t)T, w_hT, variant, st);
+  return seq_common<true>(p, w_hT, variant, st);
 }

@@ -234,6 +234,8 @@ class PinnedHostLoader:
         self.dev = [(torch.empty(shape_x, dtype=dtype, device=self.device),
                      torch.empty((self.batch_size,), dtype=torch.int64, device=self.device)) for _ in range(2)]
         self._slot = 0
+        self._pending = None
+        self._copy_stream = None
         self._i = self.per_epoch if shuffle else 0
         self.bytes_per_batch = self.dev[0][0].numel() * self.dev[0][0].element_size() + self.batch_size * 8
 
@@ -243,15 +245,42 @@ class PinnedHostLoader:
         self.x_host.copy_(xs)
         self.y_host.copy_(ys)
 
-    def next(self) -> Tuple[torch.Tensor, torch.Tensor]:
+    def _advance(self) -> int:
         if self._i >= self.per_epoch:
             if self.shuffle:
                 self._reshuffle()
             self._i = 0
         lo = self._i * self.batch_size
         self._i += 1
+        return lo
+
+    def _issue(self):
+        """Enqueue the H2D copy of the next batch on the copy stream into the free staging slot."""
+        lo = self._advance()
         dx, dy = self.dev[self._slot]
-        dx.copy_(self.x_host[lo:lo + self.batch_size], non_blocking=True)
-        dy.copy_(self.y_host[lo:lo + self.batch_size], non_blocking=True)
         self._slot ^= 1
+        if self.device.type != "cuda":
+            dx.copy_(self.x_host[lo:lo + self.batch_size])
+            dy.copy_(self.y_host[lo:lo + self.batch_size])
+            return dx, dy, None
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        # the slot being overwritten was consumed by compute work already enqueued on the current stream
+        self._copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self._copy_stream):
+            dx.copy_(self.x_host[lo:lo + self.batch_size], non_blocking=True)
+            dy.copy_(self.y_host[lo:lo + self.batch_size], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        return dx, dy, ev
+
+    def next(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Returns this step's batch (its H2D copy was enqueued one call earlier, so it overlaps the previous step's
+        compute) and enqueues the copy of the following one.  Every step still moves its own inputs host->device."""
+        if self._pending is None:
+            self._pending = self._issue()
+        dx, dy, ev = self._pending
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+        self._pending = self._issue()
         return dx, dy

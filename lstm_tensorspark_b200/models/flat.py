@@ -64,11 +64,23 @@ class FlatParams:
         new_grad.copy_(self.grad)
         self.data, self.grad = new_data, new_grad
         self._rebind()
+        self._register_shadows()
 
     def ensure_shadow(self) -> torch.Tensor:
         if self.shadow is None:
             self.shadow = self.data.to(torch.bfloat16)
+        self._register_shadows()
         return self.shadow
+
+    def _register_shadows(self):
+        """Let the CUDA ops find the maintained bf16 copy of a parameter (keyed by the fp32 view's address) instead of
+        re-casting the weights every step; also the fp32 grad view so weight-gradient GEMMs accumulate in place."""
+        if self.shadow is None or not self.data.is_cuda:
+            return
+        from ..ops import cuda_lstm
+        for p, o in zip(self.params, self.offsets):
+            cuda_lstm.register_param(p.data_ptr(), self.shadow[o:o + p.numel()].view(p.shape),
+                                     self.grad[o:o + p.numel()].view(p.shape), owner=self)
 
     def refresh_shadow(self):
         if self.shadow is not None:

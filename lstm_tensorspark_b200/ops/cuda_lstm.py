@@ -20,7 +20,49 @@ _SM_COUNT = {}
 FORCE_GENERIC = os.environ.get("LSTM_TS_FORCE_GENERIC", "0") == "1"
 SEQ_VARIANT = int(os.environ.get("LSTM_TS_SEQ_VARIANT", "0"))     # tuning knob: tiles_per_cta + 16*stages (0 = auto)
 USE_TC_GEMM = os.environ.get("LSTM_TS_TC_GEMM", "1") == "1"
+GEMM_VARIANT = int(os.environ.get("LSTM_TS_GEMM_VARIANT", "1"))   # 0: 128x128 tiles, 1: 128x256 tiles (faster on large shapes)
 STATS = {"fast_fwd": 0, "fast_bwd": 0, "generic_fwd": 0, "generic_bwd": 0, "tc_gemm": 0, "kernels": 0}
+
+
+_PARAMS = {}          # fp32 param address -> (bf16 shadow view, fp32 grad view), maintained by models.flat.FlatParams
+DIRECT_GRADS = os.environ.get("LSTM_TS_DIRECT_GRADS", "1") == "1"
+
+
+def register_param(addr: int, shadow: torch.Tensor, grad: torch.Tensor, owner=None) -> None:
+    import weakref
+    _PARAMS[addr] = (shadow, grad, weakref.ref(owner) if owner is not None else None)
+
+
+def _lookup(addr: int):
+    ent = _PARAMS.get(addr)
+    if ent is None:
+        return None
+    if ent[2] is not None and ent[2]() is None:       # the FlatParams buffer died: its address may have been reused
+        del _PARAMS[addr]
+        return None
+    return ent
+
+
+def _lowp(w: torch.Tensor, cd: torch.dtype) -> torch.Tensor:
+    """bf16 copy of a weight: the optimizer-maintained shadow when there is one, a cast otherwise."""
+    if cd == torch.bfloat16:
+        ent = _lookup(w.data_ptr())
+        if ent is not None and ent[0].shape == w.shape:
+            return ent[0]
+    return w.detach().to(cd).contiguous()
+
+
+def _accumulate_grad(w_addr: int, a_t: torch.Tensor, b: torch.Tensor):
+    """dW = a_t @ b in fp32.  When the parameter lives in a FlatParams buffer the product is accumulated straight into
+    its grad view (beta = 1 GEMM epilogue, no separate AccumulateGrad add) and None is returned to autograd."""
+    ent = _lookup(w_addr) if DIRECT_GRADS else None
+    if ent is not None and a_t.dtype == torch.bfloat16:
+        try:
+            torch.addmm(ent[1], a_t, b, out_dtype=torch.float32, out=ent[1])
+            return None
+        except (TypeError, RuntimeError):
+            pass
+    return _mm_f32(a_t, b)
 
 
 def _sync_ws(device) -> torch.Tensor:
@@ -48,10 +90,9 @@ def fast_path_supported(B: int, H: int, dtype: torch.dtype, device) -> bool:
     if FORCE_GENERIC or dtype != torch.bfloat16 or H % 64 != 0:
         return False
     tiles_m = (B + 127) // 128
-    tiles_per_cta = 2 if tiles_m % 2 == 0 else 1      # a CTA alternates two batch tiles when it can (see the kernel)
-    if (tiles_m // tiles_per_cta) * (H // 16) > _sms(device):
+    if tiles_m * (H // 16) > _sms(device):
         return False
-    smem = H * 64 * 2 + 4 * 16384 + tiles_per_cta * 16384 + 2048   # resident slice + >=4 stages + DSMEM exchange
+    smem = H * 64 * 2 + 2 * 16384 + 16384 + 2048      # resident slice + >=2 stages + DSMEM exchange (+ barriers)
     return smem <= 227 * 1024 and tiles_m <= 16
 
 
@@ -69,7 +110,7 @@ def _gemm_tn(a: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     if USE_TC_GEMM and a.dtype == torch.bfloat16 and a.shape[1] % 8 == 0 and w.shape[0] % 8 == 0 and a.shape[0] >= 128:
         STATS["tc_gemm"] += 1
         STATS["kernels"] += 1
-        return ext().gemm_bf16_tn(a.contiguous(), w.contiguous(), None, False, 0)
+        return ext().gemm_bf16_tn(a.contiguous(), w.contiguous(), None, False, GEMM_VARIANT)
     return a @ w.t()
 
 
@@ -81,8 +122,8 @@ class _LSTMSeqFn(torch.autograd.Function):
         H = w_h.shape[1]
         cd = x_seq.dtype
         x2d = x_seq.reshape(T * B, D).contiguous()
-        w_x_c = w_x.detach().to(cd).contiguous()
-        w_h_c = w_h.detach().to(cd).contiguous()
+        w_x_c = _lowp(w_x, cd)
+        w_h_c = _lowp(w_h, cd)
         bias_f = bias.detach().float().contiguous()
         gx = _gemm_tn(x2d, w_x_c).view(T, B, 4 * H)
         fast = fast_path_supported(B, H, cd, x_seq.device)
@@ -110,6 +151,7 @@ class _LSTMSeqFn(torch.autograd.Function):
         ctx.save_for_backward(x2d, h_seq, c_seq, act, w_x_c, w_h_c)
         ctx.fast = fast
         ctx.dims = (T, B, D, H)
+        ctx.w_addrs = (w_x.data_ptr(), w_h.data_ptr())
         ctx.in_dtypes = (h0.dtype, c0.dtype)
         return h_seq[1:], c_seq[T]
 
@@ -141,8 +183,8 @@ class _LSTMSeqFn(torch.autograd.Function):
             STATS["kernels"] += T
         dg2d = dpre.view(T * B, 4 * H)
         dg_t = dg2d.t()
-        dw_x = _mm_f32(dg_t, x2d)
-        dw_h = _mm_f32(dg_t, h_seq[:T].reshape(T * B, H))
+        dw_x = _accumulate_grad(ctx.w_addrs[0], dg_t, x2d)
+        dw_h = _accumulate_grad(ctx.w_addrs[1], dg_t, h_seq[:T].reshape(T * B, H))
         db = torch.sum(dg2d, dim=0, dtype=torch.float32)
         dx = None
         if ctx.needs_input_grad[0]:
