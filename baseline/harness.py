@@ -65,10 +65,25 @@ class BaselineRunner:
         dev_y = torch.as_tensor(ys).to(self.device)
         host_x = torch.as_tensor(xs).to(torch.bfloat16).pin_memory()
         host_y = torch.as_tensor(ys).pin_memory()
-        stage_x = torch.empty(B, T, D, dtype=torch.bfloat16, device=self.device)
-        stage_y = torch.empty(B, dtype=torch.int64, device=self.device)
+        stage = [(torch.empty(B, T, D, dtype=torch.bfloat16, device=self.device),
+                  torch.empty(B, dtype=torch.int64, device=self.device)) for _ in range(2)]
         loss_host = torch.empty((), dtype=torch.float32, pin_memory=True)
-        it = {"i": 0}
+        it = {"i": 0, "slot": 0, "pending": None}
+        copy_stream = torch.cuda.Stream(device=self.device)
+
+        def issue():
+            """double-buffered prefetch on a copy stream (what a careful PyTorch user does with pinned memory)"""
+            i = it["i"] % nb
+            it["i"] += 1
+            sx, sy = stage[it["slot"]]
+            it["slot"] ^= 1
+            copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(copy_stream):
+                sx.copy_(host_x[i * B:(i + 1) * B], non_blocking=True)
+                sy.copy_(host_y[i * B:(i + 1) * B], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return sx, sy, ev
 
         def step_dev():
             i = it["i"] % nb
@@ -76,11 +91,12 @@ class BaselineRunner:
             return self.train_step(dev_x[i * B:(i + 1) * B], dev_y[i * B:(i + 1) * B])
 
         def step_e2e():
-            i = it["i"] % nb
-            it["i"] += 1
-            stage_x.copy_(host_x[i * B:(i + 1) * B], non_blocking=True)
-            stage_y.copy_(host_y[i * B:(i + 1) * B], non_blocking=True)
-            loss = self.train_step(stage_x, stage_y)
+            if it["pending"] is None:
+                it["pending"] = issue()
+            sx, sy, ev = it["pending"]
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            it["pending"] = issue()
+            loss = self.train_step(sx, sy)
             loss_host.copy_(loss.float())
             return loss_host
 

@@ -188,7 +188,7 @@ def check_seq_tune():
         bias = torch.zeros(4 * H, device=dev)
         h0 = torch.zeros(B, H, device=dev).bfloat16(); c0 = torch.zeros(B, H, device=dev)
         ws = cuda_lstm._sync_ws(dev)
-        for (tiles, st, mode) in ((1, 4, 0), (1, 6, 0), (1, 6, 1), (1, 6, 2)):
+        for (tiles, st, mode) in ((1, 0, 0), (2, 0, 0), (2, 4, 0)):
             v = tiles + 16 * st + 4096 * mode
             try:
                 ms = _time_ms(lambda: E.lstm_seq_fwd(gx, whb, bias, h0, c0, ws, v), iters=5, warm=2)
@@ -217,6 +217,65 @@ def check_seq_tune():
                       accum_ns=int(d[0, 1]) - t0)
             except Exception as e:                     # noqa: BLE001
                 _emit("fwd_variant", T=T, B=B, H=H, tiles=tiles, stages=st, error=repr(e)[:300])
+
+
+def check_skew():
+    """Per-CTA time stamps at step 8 of the forward kernel: when each CTA's accumulator was ready and when it signalled."""
+    import torch
+    from lstm_tensorspark_b200.ops import cuda_lstm
+    from lstm_tensorspark_b200.ops.cuda_ext import ext
+    E = ext()
+    dev = torch.device("cuda")
+    T, B, H = 32, 256, 1024
+    gx = (torch.randn(T, B, 4 * H, device=dev) * 0.5).bfloat16()
+    whb = (torch.randn(4 * H, H, device=dev) / H ** 0.5).bfloat16()
+    bias = torch.zeros(4 * H, device=dev)
+    h0 = torch.zeros(B, H, device=dev).bfloat16(); c0 = torch.zeros(B, H, device=dev)
+    ws = cuda_lstm._sync_ws(dev)
+    for rep in range(2):
+        dbg = torch.zeros(4 * (T + 2) + 64 + 2 * 160, dtype=torch.int64, device=dev)
+        E.lstm_seq_fwd(gx, whb, bias, h0, c0, ws, 0, dbg)
+        torch.cuda.synchronize()
+        st = dbg[4 * (T + 2) + 64:].view(-1, 2)[:128].cpu()
+        acc, sig = st[:, 0], st[:, 1]
+        base = int(acc.min())
+        a = (acc - base).tolist(); g = (sig - base).tolist()
+        for mb in (0, 1):
+            aa = a[64 * mb:64 * mb + 64]; gg = g[64 * mb:64 * mb + 64]
+            _emit("skew", rep=rep, mb=mb, acc_min=min(aa), acc_max=max(aa), acc_sorted=sorted(aa)[::8], sig_min=min(gg), sig_max=max(gg),
+                  slowest=[i for i, _ in sorted(enumerate(aa), key=lambda kv: -kv[1])[:8]])
+
+
+def check_seq_tiles():
+    """Kernel time of the persistent fwd / bwd kernels with 1 vs 2 batch tiles per CTA (T=128, B=256, H=1024)."""
+    import torch
+    from lstm_tensorspark_b200.ops import cuda_lstm
+    from lstm_tensorspark_b200.ops.cuda_ext import ext
+    E = ext()
+    dev = torch.device("cuda")
+    T, B, H = 128, 256, 1024
+    torch.manual_seed(0)
+    gx = (torch.randn(T, B, 4 * H, device=dev) * 0.5).bfloat16()
+    whb = (torch.randn(4 * H, H, device=dev) / H ** 0.5).bfloat16()
+    whT = whb.t().contiguous()
+    bias = torch.zeros(4 * H, device=dev)
+    h0 = torch.zeros(B, H, device=dev).bfloat16(); c0 = torch.zeros(B, H, device=dev)
+    dh = (torch.randn(T, B, H, device=dev) * 0.1).bfloat16()
+    z = torch.zeros(B, H, device=dev)
+    ws = cuda_lstm._sync_ws(dev)
+    ref = None
+    for tiles in (1, 2):
+        hs, cs, act = E.lstm_seq_fwd(gx, whb, bias, h0, c0, ws, tiles)
+        dpre, dh0, dc0 = E.lstm_seq_bwd(dh, whT, act, cs, z, z, ws, tiles)
+        torch.cuda.synchronize()
+        cuda_lstm.check_kernel_errors(dev)
+        if ref is None:
+            ref = (hs, dpre, dh0)
+        f = _time_ms(lambda: E.lstm_seq_fwd(gx, whb, bias, h0, c0, ws, tiles), iters=5, warm=2)
+        b = _time_ms(lambda: E.lstm_seq_bwd(dh, whT, act, cs, z, z, ws, tiles), iters=5, warm=2)
+        _emit("seq_tiles", tiles=tiles, fwd_ms=f, fwd_us_per_step=f * 1e3 / T, bwd_ms=b, bwd_us_per_step=b * 1e3 / T,
+              h_same=bool(torch.equal(hs, ref[0])), dpre_maxdiff=float((dpre.float() - ref[1].float()).abs().max()),
+              dh0_maxdiff=float((dh0 - ref[2]).abs().max()))
 
 
 def check_umma():
@@ -252,7 +311,7 @@ def check_iris_gpu():
     _emit("iris_gpu_standalone", rc=r.returncode, tail=(r.stdout + r.stderr)[-600:])
 
 
-CHECKS = {"umma": check_umma, "seq_tune": check_seq_tune, "env": check_env, "simple": check_simple, "gemm": check_gemm, "generic": check_generic, "seq_small": check_seq_small,
+CHECKS = {"skew": check_skew, "seq_tiles": check_seq_tiles, "umma": check_umma, "seq_tune": check_seq_tune, "env": check_env, "simple": check_simple, "gemm": check_gemm, "generic": check_generic, "seq_small": check_seq_small,
           "seq_big": check_seq_big, "engine": check_engine, "iris_gpu": check_iris_gpu}
 
 

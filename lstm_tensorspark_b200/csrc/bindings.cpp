@@ -21,12 +21,12 @@ int ts_head_xent(const void*, const float*, const float*, const long long*, floa
                  int, cudaStream_t);
 int ts_xent_rows(const float*, const long long*, float*, float*, int*, int, int, cudaStream_t);
 int ts_flat_adam(float*, const float*, float*, float*, void*, long long, float, float, float, float, float, float,
-                 cudaStream_t);
+                 cudaStream_t, int*);
 int ts_flat_sgd(float*, const float*, void*, long long, float, float, float, cudaStream_t);
 int ts_cast_bf16(const float*, void*, long long, cudaStream_t);
 int ts_fused_allreduce(const unsigned long long*, unsigned long long, unsigned long long, unsigned long long, float*,
                        float*, unsigned int*, int*, long long, int, int, int, int, int, int, float, float, float, float,
-                       float, double, cudaStream_t);
+                       float, double, cudaStream_t, int*);
 int ts_ar_max_blocks();
 int ts_ar_flag_words();
 int ts_gemm_bf16_tn(const void*, const void*, void*, const float*, int, int, int, int, int, int, cudaStream_t);
@@ -124,12 +124,13 @@ std::vector<Tensor> xent_rows(const Tensor& logits, const Tensor& labels) {
 
 // ---- optimizer ----------------------------------------------------------------------------------------------
 void flat_adam(Tensor p, const Tensor& g, Tensor m, Tensor v, std::optional<Tensor> shadow, double lr_t, double b1,
-               double b2, double eps, double wd, double gscale) {
+               double b2, double eps, double wd, double gscale, std::optional<Tensor> step_dev) {
   chk_cuda(p, "p"); chk_cuda(g, "g"); chk_cuda(m, "m"); chk_cuda(v, "v");
   c10::cuda::CUDAGuard gd(p.device());
   TORCH_CHECK(p.numel() == g.numel() && p.numel() == m.numel() && p.numel() == v.numel(), "numel mismatch");
   check(ts_flat_adam(p.data_ptr<float>(), g.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(),
-                     shadow.has_value() ? shadow->data_ptr() : nullptr, p.numel(), lr_t, b1, b2, eps, wd, gscale, stream()),
+                     shadow.has_value() ? shadow->data_ptr() : nullptr, p.numel(), lr_t, b1, b2, eps, wd, gscale, stream(),
+                     step_dev.has_value() ? step_dev->data_ptr<int>() : nullptr),
         "flat_adam");
 }
 void flat_sgd(Tensor p, const Tensor& g, std::optional<Tensor> shadow, double lr, double wd, double gscale) {
@@ -150,7 +151,7 @@ void cast_bf16(const Tensor& p, Tensor shadow) {
 void fused_allreduce(const Tensor& ptrs, int64_t mc_in, int64_t mc_param, int64_t mc_shadow, std::optional<Tensor> m,
                      std::optional<Tensor> v, Tensor epochs, Tensor err, int64_t n, int64_t rank, int64_t world,
                      int64_t mode, bool two_shot, bool multicast, int64_t blocks, double lr, double b1, double b2,
-                     double eps, double wd, double timeout_s) {
+                     double eps, double wd, double timeout_s, std::optional<Tensor> step_dev) {
   TORCH_CHECK(!ptrs.is_cuda() && ptrs.scalar_type() == torch::kInt64 && ptrs.numel() == 4 * world, "ptrs: cpu int64 [4,world]");
   chk_cuda(epochs, "epochs"); chk_cuda(err, "err");
   c10::cuda::CUDAGuard gd(epochs.device());
@@ -158,7 +159,8 @@ void fused_allreduce(const Tensor& ptrs, int64_t mc_in, int64_t mc_param, int64_
                            (unsigned long long)mc_param, (unsigned long long)mc_shadow,
                            m.has_value() ? m->data_ptr<float>() : nullptr, v.has_value() ? v->data_ptr<float>() : nullptr,
                            (unsigned int*)epochs.data_ptr<int>(), err.data_ptr<int>(), n, (int)rank, (int)world, (int)mode,
-                           two_shot ? 1 : 0, multicast ? 1 : 0, (int)blocks, lr, b1, b2, eps, wd, timeout_s, stream()),
+                           two_shot ? 1 : 0, multicast ? 1 : 0, (int)blocks, lr, b1, b2, eps, wd, timeout_s, stream(),
+                           step_dev.has_value() ? step_dev->data_ptr<int>() : nullptr),
         "fused_allreduce");
 }
 
@@ -231,10 +233,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("lstm_pointwise_bwd", &lstm_pointwise_bwd);
   m.def("head_xent", &head_xent);
   m.def("xent_rows", &xent_rows);
-  m.def("flat_adam", &flat_adam);
+  m.def("flat_adam", &flat_adam, py::arg("p"), py::arg("g"), py::arg("m"), py::arg("v"), py::arg("shadow"), py::arg("lr_t"),
+        py::arg("b1"), py::arg("b2"), py::arg("eps"), py::arg("wd"), py::arg("gscale"), py::arg("step_dev") = py::none());
   m.def("flat_sgd", &flat_sgd);
   m.def("cast_bf16", &cast_bf16);
-  m.def("fused_allreduce", &fused_allreduce);
+  m.def("fused_allreduce", &fused_allreduce, py::arg("ptrs"), py::arg("mc_in"), py::arg("mc_param"), py::arg("mc_shadow"), py::arg("m"),
+        py::arg("v"), py::arg("epochs"), py::arg("err"), py::arg("n"), py::arg("rank"), py::arg("world"), py::arg("mode"),
+        py::arg("two_shot"), py::arg("multicast"), py::arg("blocks"), py::arg("lr"), py::arg("b1"), py::arg("b2"), py::arg("eps"),
+        py::arg("wd"), py::arg("timeout_s"), py::arg("step_dev") = py::none());
   m.def("ar_max_blocks", []() { return ts_ar_max_blocks(); });
   m.def("ar_flag_words", []() { return ts_ar_flag_words(); });
   m.def("gemm_bf16_tn", &gemm_bf16_tn);

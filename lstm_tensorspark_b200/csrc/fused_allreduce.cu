@@ -42,6 +42,7 @@ struct ARArgs {
   float* v;
   uint32_t* epochs;            // local [kMaxBlocks] barrier epochs
   int* err;                    // local error flag (1 = barrier timeout)
+  int* step_dev;               // Adam: device-resident step counter (graph-replay safe); null -> lr is already corrected
   long long n4;                // message length in float4
   int rank, world;
   float inv_world, lr, b1, b2, eps, wd;
@@ -110,14 +111,14 @@ TS_DEVICE void cross_rank_barrier(const ARArgs& a, uint32_t epoch) {
 }
 
 template <int kMode>
-TS_DEVICE float4 apply_update(const ARArgs& a, float4 sum, long long i, float4 w) {
+TS_DEVICE float4 apply_update(const ARArgs& a, float4 sum, long long i, float4 w, float lr) {
   float4 g;
   g.x = sum.x * a.inv_world; g.y = sum.y * a.inv_world; g.z = sum.z * a.inv_world; g.w = sum.w * a.inv_world;
   if (kMode == MODE_AVG) return g;
   float* wp = &w.x; float* gp = &g.x;
   if (kMode == MODE_SGD) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) wp[k] -= a.lr * (gp[k] + a.wd * wp[k]);
+    for (int k = 0; k < 4; ++k) wp[k] -= lr * (gp[k] + a.wd * wp[k]);
     return w;
   }
   float4 mv = reinterpret_cast<float4*>(a.m)[i], vv = reinterpret_cast<float4*>(a.v)[i];
@@ -127,7 +128,7 @@ TS_DEVICE float4 apply_update(const ARArgs& a, float4 sum, long long i, float4 w
     float gg = gp[k] + a.wd * wp[k];
     mp[k] = a.b1 * mp[k] + (1.f - a.b1) * gg;
     vp[k] = a.b2 * vp[k] + (1.f - a.b2) * gg * gg;
-    wp[k] -= a.lr * mp[k] / (sqrtf(vp[k]) + a.eps);      // a.lr is the bias-corrected lr_t
+    wp[k] -= lr * mp[k] / (sqrtf(vp[k]) + a.eps);        // lr is the bias-corrected lr_t
   }
   reinterpret_cast<float4*>(a.m)[i] = mv;
   reinterpret_cast<float4*>(a.v)[i] = vv;
@@ -137,15 +138,42 @@ TS_DEVICE float4 apply_update(const ARArgs& a, float4 sum, long long i, float4 w
 // ---------------------------------------------------------------------------------------------------------
 // two-shot
 // ---------------------------------------------------------------------------------------------------------
+TS_DEVICE float effective_lr(const ARArgs& a) {
+  if (a.step_dev == nullptr) return a.lr;
+  const float t = (float)(*a.step_dev);
+  return a.lr * sqrtf(1.f - powf(a.b2, t)) / (1.f - powf(a.b1, t));
+}
+__global__ void ar_inc_step_kernel(int* step) { *step += 1; }
+
 template <int kMode, bool kMulticast>
 __global__ void __launch_bounds__(kThreads) ar_two_shot_kernel(const __grid_constant__ ARArgs a) {
+  const float lr = kMode == MODE_ADAM ? effective_lr(a) : a.lr;
   uint32_t epoch = a.epochs[blockIdx.x];
   cross_rank_barrier(a, ++epoch);              // every rank's inputs are final
 
   long long per = (a.n4 + a.world - 1) / a.world;
   long long lo = per * a.rank, hi = lo + per < a.n4 ? lo + per : a.n4;
   long long stride = (long long)gridDim.x * kThreads;
-  for (long long i = lo + (long long)blockIdx.x * kThreads + threadIdx.x; i < hi; i += stride) {
+  long long i = lo + (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (kMulticast) {
+    // 4 independent switch reductions in flight per thread (NVLink round trips are ~2 us: memory-level parallelism,
+    // not thread count, sets the bandwidth of the large-message regime)
+    for (; i + 3 * stride < hi; i += 4 * stride) {
+      float4 s4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s4[u] = mc_ld_reduce_f4(a.mc_in + 4 * (i + u * stride));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long j = i + u * stride;
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kMode != MODE_AVG) w = reinterpret_cast<const float4*>(a.param[a.rank])[j];
+        const float4 nw = apply_update<kMode>(a, s4[u], j, w, lr);
+        mc_st_f4(a.mc_param + 4 * j, nw);
+        if (a.mc_shadow) mc_st_bf16x4(a.mc_shadow + 4 * j, pack_bf16x4(nw));
+      }
+    }
+  }
+  for (; i < hi; i += stride) {
     float4 sum;
     if (kMulticast) {
       sum = mc_ld_reduce_f4(a.mc_in + 4 * i);
@@ -161,7 +189,7 @@ __global__ void __launch_bounds__(kThreads) ar_two_shot_kernel(const __grid_cons
     }
     float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
     if (kMode != MODE_AVG) w = reinterpret_cast<const float4*>(a.param[a.rank])[i];
-    float4 nw = apply_update<kMode>(a, sum, i, w);
+    float4 nw = apply_update<kMode>(a, sum, i, w, lr);
     uint2 sh = pack_bf16x4(nw);
     if (kMulticast) {
       mc_st_f4(a.mc_param + 4 * i, nw);
@@ -184,6 +212,7 @@ __global__ void __launch_bounds__(kThreads) ar_two_shot_kernel(const __grid_cons
 // ---------------------------------------------------------------------------------------------------------
 template <int kMode>
 __global__ void __launch_bounds__(kThreads) ar_one_shot_kernel(const __grid_constant__ ARArgs a) {
+  const float lr = kMode == MODE_ADAM ? effective_lr(a) : a.lr;
   uint32_t epoch = a.epochs[blockIdx.x];
   long long stride = (long long)gridDim.x * kThreads;
   long long first = (long long)blockIdx.x * kThreads + threadIdx.x;
@@ -204,7 +233,7 @@ __global__ void __launch_bounds__(kThreads) ar_one_shot_kernel(const __grid_cons
       if (r < a.world) { sum.x += part[r].x; sum.y += part[r].y; sum.z += part[r].z; sum.w += part[r].w; }
     float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
     if (kMode != MODE_AVG) w = reinterpret_cast<const float4*>(my_param)[i];
-    float4 nw = apply_update<kMode>(a, sum, i, w);
+    float4 nw = apply_update<kMode>(a, sum, i, w, lr);
     reinterpret_cast<float4*>(my_param)[i] = nw;
     if (a.shadow[a.rank]) reinterpret_cast<uint2*>(a.shadow[a.rank])[i] = pack_bf16x4(nw);
   }
@@ -230,7 +259,7 @@ extern "C" int ts_fused_allreduce(const unsigned long long* ptrs, unsigned long 
                                   unsigned long long mc_shadow, float* m, float* v, unsigned int* epochs, int* err,
                                   long long n, int rank, int world, int mode, int two_shot, int multicast, int blocks,
                                   float lr, float b1, float b2, float eps, float wd, double timeout_s,
-                                  cudaStream_t st) {
+                                  cudaStream_t st, int* step_dev) {
   if (world > kMaxRanks || world < 1 || n % 4 != 0) return -2;
   if (blocks > kMaxBlocks) blocks = kMaxBlocks;
   if (blocks < 1) blocks = 1;
@@ -242,7 +271,8 @@ extern "C" int ts_fused_allreduce(const unsigned long long* ptrs, unsigned long 
     a.flags[r] = r < world ? (uint32_t*)ptrs[3 * world + r] : nullptr;
   }
   a.mc_in = (float*)mc_in; a.mc_param = (float*)mc_param; a.mc_shadow = (__nv_bfloat16*)mc_shadow;
-  a.m = m; a.v = v; a.epochs = epochs; a.err = err;
+  a.m = m; a.v = v; a.epochs = epochs; a.err = err; a.step_dev = (mode == MODE_ADAM) ? step_dev : nullptr;
+  if (a.step_dev) ar_inc_step_kernel<<<1, 1, 0, st>>>(a.step_dev);
   a.n4 = n / 4; a.rank = rank; a.world = world; a.inv_world = 1.0f / (float)world;
   a.lr = lr; a.b1 = b1; a.b2 = b2; a.eps = eps; a.wd = wd;
   a.timeout_ns = (unsigned long long)(timeout_s * 1e9);

@@ -172,7 +172,10 @@ struct SeqParams {
 // The two role warps run CONVERGED and issue under elect.sync so descriptors / addresses stay in uniform registers;
 // k-blocks are handled in pairs (two overlapped mbarrier.try_wait, 8 MMAs per turn): the barrier turn-around, not the
 // tensor pipe (48 cycles per M128xN64xK16 instruction), is what bounds a step.
-template <bool kBwd, int kStages>
+// kTiles = 2: the CTA alternates TWO independent 128-row batch tiles (same resident weight slice): while one tile sits
+// in its epilogue + grid barrier (latency), the other one streams its operand and runs its MMAs.  Half as many CTAs are
+// needed (64 for B = 256, H = 1024), which leaves SMs free for the weight-gradient GEMMs that run concurrently.
+template <bool kBwd, int kStages, int kTiles>
 __global__ void __launch_bounds__(384, 1)
 lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -181,15 +184,14 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
   uint8_t* smem_w = smem;                                    // resident weight slice: num_kb blocks of [64 x 64]
   uint8_t* smem_a = smem + (size_t)num_kb * kWBlockBytes;    // kStages x 16 KB
   uint8_t* smem_x = smem_a + kStages * kABytes;              // backward: DSMEM exchange buffer (bf16)
-  SeqSmem* ss = reinterpret_cast<SeqSmem*>(smem_x + (kBwd ? kXchgBytes : 0));
+  SeqSmem* ss = reinterpret_cast<SeqSmem*>(smem_x + (kBwd ? kTiles * kXchgBytes : 0));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mb = blockIdx.x / p.tiles_n;
+  const int mb0 = (blockIdx.x / p.tiles_n) * kTiles;          // first batch tile of this CTA
   const int in_mb = blockIdx.x % p.tiles_n;
   const uint32_t crank = kBwd ? cluster_ctarank() : 0;
   const int nb = kBwd ? in_mb / 4 : in_mb;
   const int ks = kBwd ? (int)crank : 0;
-  unsigned int* counter = p.sync + mb;
   volatile int* abort_flag = &ss->abort_flag;
   const int steps = kBwd ? p.T + 1 : p.T;                    // backward runs one extra GEMM to produce dh_0
 
@@ -198,12 +200,12 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
     tc::prefetch_tmap(&tmap_w);
     for (int s = 0; s < kStages; ++s) { tc::mbar_init(&ss->full[s], 1); tc::mbar_init(&ss->empty[s], 1); }
     tc::mbar_init(&ss->w_full, 1);
-    tc::mbar_init(&ss->tmem_full[0], 1);
-    tc::mbar_init(&ss->xchg_full[0], 4);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&ss->tmem_full[i], 1); tc::mbar_init(&ss->xchg_full[i], 4); }
     tc::fence_barrier_init();
   }
   if (!kBwd && threadIdx.x >= 64 && threadIdx.x < 128) ss->bias[threadIdx.x - 64] = p.bias[nb * BN + threadIdx.x - 64];
-  if (warp == 2) { tc::tmem_alloc(&ss->tmem_slot, 64); tc::tmem_relinquish(); }
+  constexpr uint32_t kTmemCols = kTiles == 2 ? 128 : 64;
+  if (warp == 2) { tc::tmem_alloc(&ss->tmem_slot, kTmemCols); tc::tmem_relinquish(); }
   tc::fence_before_sync();
   __syncthreads();
   if (kBwd) cluster_sync_all();                 // peers' mbarriers are initialised before anyone arrives remotely
@@ -266,27 +268,33 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
     };
     for (int s = kBwd ? 1 : 0; s < steps && ok; ++s) {
       const int tsl = kBwd ? p.T - s : s;       // forward step s consumes h_seq[s]; backward iteration s consumes dG[T-s]
-      if (s > 0) ok = wait_counter(counter, (unsigned)s * p.tiles_n, abort_flag);
-      asm volatile("fence.proxy.async.global;" ::: "memory");
-      if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[4 * s + 0] = gtime();
-      const __nv_bfloat16* src = p.a_tiled + (((size_t)tsl * p.tiles_m + mb) * nkb_all + (kBwd ? ks * num_kb : 0)) * (BM * BK);
-      for (int pr = 0; pr < pairs && ok; ++pr, src += 2 * BM * BK) ok = load_pair(src);
-      if (odd && ok) ok = load_block(src);
+      for (int tile = 0; tile < kTiles && ok; ++tile) {
+        const int mb = mb0 + tile;
+        if (s > 0) ok = wait_counter(p.sync + mb, (unsigned)s * p.tiles_n, abort_flag);
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        if (p.dbg && blockIdx.x == 0 && lane == 0 && tile == 0) p.dbg[4 * s + 0] = gtime();
+        const __nv_bfloat16* src = p.a_tiled + (((size_t)tsl * p.tiles_m + mb) * nkb_all + (kBwd ? ks * num_kb : 0)) * (BM * BK);
+        for (int pr = 0; pr < pairs && ok; ++pr, src += 2 * BM * BK) ok = load_pair(src);
+        if (odd && ok) ok = load_block(src);
+      }
     }
   } else if (warp == 1) {
     // ======================================================================== MMA issuer
     constexpr uint32_t idesc = tc::make_idesc_bf16_f32(BM, BN);
     bool ok = wait_bar<false>(&ss->w_full, 0, abort_flag);
     const uint32_t full0 = tc::smem_u32(&ss->full[0]), empty0 = tc::smem_u32(&ss->empty[0]);
-    const uint32_t tfull = tc::smem_u32(&ss->tmem_full[0]);
+    const uint32_t tfull0 = tc::smem_u32(&ss->tmem_full[0]);
     const uint64_t desc_a0 = tc::desc_kmajor_sw128(tc::smem_u32(smem_a));      // + stage * (kABytes >> 4)
     const uint64_t desc_w0 = tc::desc_kmajor_sw128(tc::smem_u32(smem_w));      // + kb * (kWBlockBytes >> 4)
     uint32_t stage = 0, phase = 0;
     const bool prof = p.dbg && blockIdx.x == 0;
     constexpr int kGroup = kStages >= 5 ? 4 : 2;              // k-blocks per turn: all their try_waits are in flight together
     for (int s = kBwd ? 1 : 0; s < steps && ok; ++s) {
+     long long t_wait = 0, t_begin = prof ? clock64() : 0, t_first = 0;
+     for (int tile = 0; tile < kTiles && ok; ++tile) {
       uint64_t db = desc_w0;
-      long long t_wait = 0, t_begin = prof ? clock64() : 0, t_first = 0;
+      const uint32_t acc = tmem_d + tile * BN;
+      const uint32_t tfull = tfull0 + 8 * tile;
       for (int kb = 0; kb < num_kb && ok; kb += kGroup) {
         const int g = (num_kb - kb) < kGroup ? (num_kb - kb) : kGroup;
         uint32_t st[kGroup], ph[kGroup];
@@ -306,7 +314,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
         for (int i = 0; i < kGroup; ++i)
           if (ok && !rdy[i]) ok = wait_bar<false>(&ss->full[st[i]], ph[i], abort_flag);
         if (!ok) break;
-        if (prof) { const long long tw1 = clock64(); if (kb == 0) t_first = tw1 - tw0; else t_wait += tw1 - tw0; }
+        if (prof) { const long long tw1 = clock64(); if (kb == 0 && tile == 0) t_first = tw1 - tw0; else t_wait += tw1 - tw0; }
         tc::fence_after_sync();
         if (tc::elect_one()) {
 #pragma unroll
@@ -317,15 +325,15 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
               } else {
                 const uint64_t da = desc_a0 + (uint64_t)(st[i] * (kABytes >> 4));
                 const uint64_t dbi = db + (uint64_t)(i * (kWBlockBytes >> 4));
-                if (kb == 0 && i == 0) tc::mma_bf16_ss_first(tmem_d, da, dbi, idesc); else tc::mma_bf16_ss_acc(tmem_d, da, dbi, idesc);
-                tc::mma_bf16_ss_acc(tmem_d, da + 2, dbi + 2, idesc);
-                tc::mma_bf16_ss_acc(tmem_d, da + 4, dbi + 4, idesc);
-                tc::mma_bf16_ss_acc(tmem_d, da + 6, dbi + 6, idesc);
+                if (kb == 0 && i == 0) tc::mma_bf16_ss_first(acc, da, dbi, idesc); else tc::mma_bf16_ss_acc(acc, da, dbi, idesc);
+                tc::mma_bf16_ss_acc(acc, da + 2, dbi + 2, idesc);
+                tc::mma_bf16_ss_acc(acc, da + 4, dbi + 4, idesc);
+                tc::mma_bf16_ss_acc(acc, da + 6, dbi + 6, idesc);
                 tc::mma_commit_u32(empty0 + 8 * st[i]);
               }
             }
           }
-          if (kb + g >= num_kb) { if (p.debug_mode == 2) tc::mbar_arrive(&ss->tmem_full[0]); else tc::mma_commit_u32(tfull); }
+          if (kb + g >= num_kb) { if (p.debug_mode == 2) tc::mbar_arrive(&ss->tmem_full[tile]); else tc::mma_commit_u32(tfull); }
         }
         __syncwarp();
         db += (uint64_t)(g * (kWBlockBytes >> 4));
@@ -333,218 +341,234 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
         for (int i = 0; i < kGroup; ++i)
           if (i < g) { if (++stage == kStages) { stage = 0; phase ^= 1; } }
       }
+     }
       if (prof && lane == 0) {           // [first-turn wait (incl. grid barrier + first loads), later waits, whole step] in cycles
         p.dbg[4 * s + 3] = (unsigned long long)t_first | ((unsigned long long)t_wait << 20) | ((unsigned long long)(clock64() - t_begin) << 40);
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ======================================================================== epilogue (8 warps)
+    // ======================================================================== epilogue (8 warps, serves the tiles in turn)
     const int ewi = warp - kEpiWarp0;
     const int quarter = ewi & 3, half = ewi >> 2;
     const int rloc = quarter * 32 + lane;
     const int etid = ewi * 32 + lane;
-    const int row = mb * BM + rloc;
-    const bool valid = row < p.B;
     const int H = p.H, B = p.B;
-    const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + 32 * half;
-    uint64_t* tfull = &ss->tmem_full[0];
+    const uint32_t taddr0 = tmem_d + ((uint32_t)(quarter * 32) << 16) + 32 * half;
     uint32_t tphase = 0;
     bool ok = true;
     const bool dbg_thread = p.dbg && blockIdx.x == 0 && etid == 0;
     auto epi_bar = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
-    // grid-barrier arrive: the CTA barrier orders every epilogue thread's writes before this thread's fence + release
-    // (same pattern as cooperative-groups grid sync), the proxy fence covers the async-proxy (bulk copy) readers
-    auto signal = [&]() {
-      // ONE gpu-scope release (each fence is a full L2 round trip, ~0.8 us: three of them used to dominate the
-      // epilogue); the generic->async proxy fence is on the consumer side, after its acquire
-      signal_counter(counter);
-    };
+    // grid-barrier arrive: the CTA barrier orders every epilogue thread's writes before this thread's release
+    // (same pattern as cooperative-groups grid sync).  ONE gpu-scope release: each fence is a full L2 round trip
+    // (~0.8 us) and three of them used to dominate the epilogue; the generic->async proxy fence is on the consumer side.
 
     if (!kBwd) {
       const int j0 = nb * 16 + 8 * half;            // this thread's 8 hidden units
       const int n0 = nb * 64 + 32 * half;           // = its 32 gate columns
       const float* bs = ss->bias + 32 * half;
       for (int t = 0; t < p.T && ok; ++t) {
-        // operands that do not depend on the GEMM: issue their loads before waiting on the accumulator
-        uint4 gxv[4];
-        float4 cv[2];
-        if (valid) {
-          const __nv_bfloat16* gp = p.gx + ((size_t)t * B + row) * (4 * H) + n0;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) gxv[i] = ldg_nc16(gp + 8 * i);
-          const float* cp = p.c_seq + ((size_t)t * B + row) * H + j0;
-          cv[0] = *reinterpret_cast<const float4*>(cp); cv[1] = *reinterpret_cast<const float4*>(cp + 4);
-          if (t + 2 < p.T) prefetch_l2(gp + (size_t)2 * B * (4 * H));       // the x-projection comes from HBM: pull it into L2 early
+        for (int tile = 0; tile < kTiles; ++tile) {
+          const int mb = mb0 + tile;
+          const int row = mb * BM + rloc;
+          const bool valid = row < B;
+          // operands that do not depend on the GEMM: issue their loads before waiting on the accumulator
+          uint4 gxv[4];
+          float4 cv[2];
+          if (valid) {
+            const __nv_bfloat16* gp = p.gx + ((size_t)t * B + row) * (4 * H) + n0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) gxv[i] = ldg_nc16(gp + 8 * i);
+            const float* cp = p.c_seq + ((size_t)t * B + row) * H + j0;
+            cv[0] = *reinterpret_cast<const float4*>(cp); cv[1] = *reinterpret_cast<const float4*>(cp + 4);
+            if (t + 2 < p.T) prefetch_l2(gp + (size_t)2 * B * (4 * H));     // the x-projection comes from HBM: pull it into L2 early
+          }
+          ok = wait_bar<false>(&ss->tmem_full[tile], tphase, abort_flag);
+          if (!ok) break;
+          tc::fence_after_sync();
+          unsigned long long t_acc = 0;
+          if (p.dbg && t == 8 && etid == 0) t_acc = gtime();
+          if (dbg_thread && tile == 0) p.dbg[4 * t + 1] = gtime();
+          uint32_t v[32];
+          tc::tmem_ld32(taddr0 + tile * BN, v);
+          tc::tmem_ld_wait();
+          tc::fence_before_sync();
+          if (dbg_thread && t == 8 && tile == 0) p.dbg[4 * (p.T + 2) + 0] = gtime();
+          float cn[8], hv[8];
+          uint32_t apk[16];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const uint4 g4 = gxv[jj >> 1];
+            const uint32_t ga = (jj & 1) ? g4.z : g4.x, gb = (jj & 1) ? g4.w : g4.y;
+            const float pi = __uint_as_float(v[4 * jj + 0]) + bf_lo(ga) + bs[4 * jj + 0];
+            const float pf = __uint_as_float(v[4 * jj + 1]) + bf_hi(ga) + bs[4 * jj + 1];
+            const float pg = __uint_as_float(v[4 * jj + 2]) + bf_lo(gb) + bs[4 * jj + 2];
+            const float po = __uint_as_float(v[4 * jj + 3]) + bf_hi(gb) + bs[4 * jj + 3];
+            const float ig = ts::sigmoidf_fast(pi), fg = ts::sigmoidf_fast(pf), gg = ts::tanhf_fast(pg), og = ts::sigmoidf_fast(po);
+            const float c = fg * reinterpret_cast<const float*>(cv)[jj] + ig * gg;
+            cn[jj] = c;
+            hv[jj] = og * ts::tanhf_fast(c);
+            apk[2 * jj] = pack_bf2(ig, fg);
+            apk[2 * jj + 1] = pack_bf2(gg, og);
+          }
+          const uint4 h8 = make_uint4(pack_bf2(hv[0], hv[1]), pack_bf2(hv[2], hv[3]), pack_bf2(hv[4], hv[5]), pack_bf2(hv[6], hv[7]));
+          {
+            // next step's operand first (the only thing other CTAs wait for): 8 values = one 16 B chunk of the swizzled
+            // tile image; chunk c of row r sits at position c ^ (r & 7)
+            const size_t blk = ((size_t)(t + 1) * p.tiles_m + mb) * (H / BK) + (j0 / BK);
+            const int chunk = ((j0 % BK) / 8) ^ (rloc & 7);
+            stg16(p.a_tiled + blk * (BM * BK) + rloc * BK + chunk * 8, h8);
+          }
+          if (dbg_thread && t == 8 && tile == 0) p.dbg[4 * (p.T + 2) + 1] = gtime();
+          epi_bar();
+          if (etid == 0) {
+            if (dbg_thread && t == 8 && tile == 0) p.dbg[4 * (p.T + 2) + 2] = gtime();
+            if (p.dbg && t == 8 && tile == 0) {                // per-CTA stamps (skew study): accumulator ready / about to signal
+              p.dbg[4 * (p.T + 2) + 64 + 2 * blockIdx.x] = t_acc;
+              p.dbg[4 * (p.T + 2) + 64 + 2 * blockIdx.x + 1] = gtime();
+            }
+            signal_counter(p.sync + mb);
+            if (dbg_thread && tile == 0) p.dbg[4 * t + 2] = gtime();
+          }
+          if (valid) {                                   // everything below is off the critical path
+            stg16(p.h_seq + ((size_t)(t + 1) * B + row) * H + j0, h8);
+            float* cp = p.c_seq + ((size_t)(t + 1) * B + row) * H + j0;
+            *reinterpret_cast<float4*>(cp) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+            *reinterpret_cast<float4*>(cp + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+            __nv_bfloat16* ap = p.act + ((size_t)t * B + row) * (4 * H) + n0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) stg16(ap + 8 * i, make_uint4(apk[4 * i], apk[4 * i + 1], apk[4 * i + 2], apk[4 * i + 3]));
+          }
         }
-        ok = wait_bar<false>(tfull, tphase, abort_flag);
         tphase ^= 1;
-        if (!ok) break;
-        tc::fence_after_sync();
-        if (dbg_thread) p.dbg[4 * t + 1] = gtime();
-        uint32_t v[32];
-        tc::tmem_ld32(taddr, v);
-        tc::tmem_ld_wait();
-        tc::fence_before_sync();
-        if (dbg_thread && t == 8) p.dbg[4 * (p.T + 2) + 0] = gtime();
-        float cn[8], hv[8];
-        uint32_t apk[16];
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const uint4 g4 = gxv[jj >> 1];
-          const uint32_t ga = (jj & 1) ? g4.z : g4.x, gb = (jj & 1) ? g4.w : g4.y;
-          const float pi = __uint_as_float(v[4 * jj + 0]) + bf_lo(ga) + bs[4 * jj + 0];
-          const float pf = __uint_as_float(v[4 * jj + 1]) + bf_hi(ga) + bs[4 * jj + 1];
-          const float pg = __uint_as_float(v[4 * jj + 2]) + bf_lo(gb) + bs[4 * jj + 2];
-          const float po = __uint_as_float(v[4 * jj + 3]) + bf_hi(gb) + bs[4 * jj + 3];
-          const float ig = ts::sigmoidf_fast(pi), fg = ts::sigmoidf_fast(pf), gg = ts::tanhf_fast(pg), og = ts::sigmoidf_fast(po);
-          const float c = fg * reinterpret_cast<const float*>(cv)[jj] + ig * gg;
-          cn[jj] = c;
-          hv[jj] = og * ts::tanhf_fast(c);
-          apk[2 * jj] = pack_bf2(ig, fg);
-          apk[2 * jj + 1] = pack_bf2(gg, og);
-        }
-        const uint4 h8 = make_uint4(pack_bf2(hv[0], hv[1]), pack_bf2(hv[2], hv[3]), pack_bf2(hv[4], hv[5]), pack_bf2(hv[6], hv[7]));
-        {
-          // next step's operand first (the only thing other CTAs wait for): 8 values = one 16 B chunk of the swizzled
-          // tile image; chunk c of row r sits at position c ^ (r & 7)
-          const size_t blk = ((size_t)(t + 1) * p.tiles_m + mb) * (H / BK) + (j0 / BK);
-          const int chunk = ((j0 % BK) / 8) ^ (rloc & 7);
-          stg16(p.a_tiled + blk * (BM * BK) + rloc * BK + chunk * 8, h8);
-        }
-        if (dbg_thread && t == 8) p.dbg[4 * (p.T + 2) + 1] = gtime();
-        epi_bar();
-        if (etid == 0) {
-          if (dbg_thread && t == 8) p.dbg[4 * (p.T + 2) + 2] = gtime();
-          signal();
-          if (dbg_thread) p.dbg[4 * t + 2] = gtime();
-        }
-        if (valid) {                                   // everything below is off the critical path
-          stg16(p.h_seq + ((size_t)(t + 1) * B + row) * H + j0, h8);
-          float* cp = p.c_seq + ((size_t)(t + 1) * B + row) * H + j0;
-          *reinterpret_cast<float4*>(cp) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-          *reinterpret_cast<float4*>(cp + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
-          __nv_bfloat16* ap = p.act + ((size_t)t * B + row) * (4 * H) + n0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) stg16(ap + 8 * i, make_uint4(apk[4 * i], apk[4 * i + 1], apk[4 * i + 2], apk[4 * i + 3]));
-        }
       }
     } else {
       // after the reduce-scatter this cluster member owns hidden [64 nb + 16 ks, +16); this thread 8 of them
       const int j0 = nb * 64 + ks * 16 + 8 * half;
-      const uint32_t xbase = tc::smem_u32(smem_x);                // [4 src][128 rows][16 bf16]
-      const uint32_t xbar = tc::smem_u32(&ss->xchg_full[0]);
       uint32_t xphase = 0;
-      float dc[8], dh[8];
-      if (valid) {
+      float dc[kTiles][8], dh[kTiles][8];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          float4 a = *reinterpret_cast<const float4*>(p.dc0 + (size_t)row * H + j0 + 4 * i);
-          float4 b = *reinterpret_cast<const float4*>(p.dh0 + (size_t)row * H + j0 + 4 * i);
-          dc[4 * i] = a.x; dc[4 * i + 1] = a.y; dc[4 * i + 2] = a.z; dc[4 * i + 3] = a.w;
-          dh[4 * i] = b.x; dh[4 * i + 1] = b.y; dh[4 * i + 2] = b.z; dh[4 * i + 3] = b.w;
+      for (int tile = 0; tile < kTiles; ++tile) {
+        const int row = (mb0 + tile) * BM + rloc;
+        if (row < B) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            float4 a = *reinterpret_cast<const float4*>(p.dc0 + (size_t)row * H + j0 + 4 * i);
+            float4 b = *reinterpret_cast<const float4*>(p.dh0 + (size_t)row * H + j0 + 4 * i);
+            dc[tile][4 * i] = a.x; dc[tile][4 * i + 1] = a.y; dc[tile][4 * i + 2] = a.z; dc[tile][4 * i + 3] = a.w;
+            dh[tile][4 * i] = b.x; dh[tile][4 * i + 1] = b.y; dh[tile][4 * i + 2] = b.z; dh[tile][4 * i + 3] = b.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { dc[tile][i] = 0.f; dh[tile][i] = 0.f; }
         }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { dc[i] = 0.f; dh[i] = 0.f; }
       }
       for (int s = 0; s <= p.T && ok; ++s) {
         const int t = p.T - 1 - s;
-        uint4 av[4], dhv;
-        float4 cpv[2], cnv[2];
-        if (valid && s < p.T) {
-          const __nv_bfloat16* ap = p.act + ((size_t)t * B + row) * (4 * H) + 4 * j0;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) av[i] = ldg_nc16(ap + 8 * i);
-          dhv = ldg_nc16(p.dh_seq + ((size_t)t * B + row) * H + j0);
-          const float* c0p = p.c_seq + ((size_t)t * B + row) * H + j0;
-          const float* c1p = p.c_seq + ((size_t)(t + 1) * B + row) * H + j0;
-          cpv[0] = *reinterpret_cast<const float4*>(c0p); cpv[1] = *reinterpret_cast<const float4*>(c0p + 4);
-          cnv[0] = *reinterpret_cast<const float4*>(c1p); cnv[1] = *reinterpret_cast<const float4*>(c1p + 4);
-          if (t >= 2) {                                                        // saved activations come from HBM: pull t-2 into L2 early
-            prefetch_l2(ap - (size_t)2 * B * (4 * H));
-            prefetch_l2(c0p - (size_t)2 * B * H);
-            prefetch_l2(p.dh_seq + ((size_t)(t - 2) * B + row) * H + j0);
-          }
-        }
-        if (s > 0) {
-          ok = wait_bar<false>(tfull, tphase, abort_flag);
-          tphase ^= 1;
-          if (!ok) break;
-          tc::fence_after_sync();
-          if (dbg_thread) p.dbg[4 * s + 1] = gtime();
-          uint32_t v[32];
-          tc::tmem_ld32(taddr, v);
-          tc::tmem_ld_wait();
-          tc::fence_before_sync();
-          // reduce-scatter over the 4 K-quarters: column chunk q (16 wide, bf16) goes to member q's slot [ks] (DSMEM)
+        for (int tile = 0; tile < kTiles; ++tile) {
+          const int mb = mb0 + tile;
+          const int row = mb * BM + rloc;
+          const bool valid = row < B;
+          uint8_t* xbuf = smem_x + tile * kXchgBytes;               // [4 src][128 rows][16 bf16]
+          const uint32_t xbase = tc::smem_u32(xbuf);
+          const uint32_t xbar = tc::smem_u32(&ss->xchg_full[tile]);
+          uint4 av[4], dhv;
+          float4 cpv[2], cnv[2];
+          if (valid && s < p.T) {
+            const __nv_bfloat16* ap = p.act + ((size_t)t * B + row) * (4 * H) + 4 * j0;
 #pragma unroll
-          for (int qq = 0; qq < 2; ++qq) {
-            const uint32_t dst = mapa(xbase + (uint32_t)((ks * BM + rloc) * 32), (uint32_t)(2 * half + qq));
-            uint32_t pk[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) pk[i] = pack_bf2(__uint_as_float(v[16 * qq + 2 * i]), __uint_as_float(v[16 * qq + 2 * i + 1]));
-            st_cluster_u4(dst, make_uint4(pk[0], pk[1], pk[2], pk[3]));
-            st_cluster_u4(dst + 16, make_uint4(pk[4], pk[5], pk[6], pk[7]));
-          }
-          epi_bar();
-          if (etid < 4) mbar_arrive_remote(mapa(xbar, (uint32_t)etid));
-          ok = wait_bar<true>(&ss->xchg_full[0], xphase, abort_flag);
-          xphase ^= 1;
-          if (!ok) break;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) dh[i] = 0.f;
-#pragma unroll
-          for (int src = 0; src < 4; ++src) {
-            const uint4 x4 = *reinterpret_cast<const uint4*>(smem_x + (size_t)(src * BM + rloc) * 32 + 16 * half);
-            const uint32_t w[4] = {x4.x, x4.y, x4.z, x4.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { dh[2 * i] += bf_lo(w[i]); dh[2 * i + 1] += bf_hi(w[i]); }
-          }
-        }
-        if (s == p.T) {
-          if (valid) {
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              *reinterpret_cast<float4*>(p.dh0 + (size_t)row * H + j0 + 4 * i) = make_float4(dh[4 * i], dh[4 * i + 1], dh[4 * i + 2], dh[4 * i + 3]);
-              *reinterpret_cast<float4*>(p.dc0 + (size_t)row * H + j0 + 4 * i) = make_float4(dc[4 * i], dc[4 * i + 1], dc[4 * i + 2], dc[4 * i + 3]);
+            for (int i = 0; i < 4; ++i) av[i] = ldg_nc16(ap + 8 * i);
+            dhv = ldg_nc16(p.dh_seq + ((size_t)t * B + row) * H + j0);
+            const float* c0p = p.c_seq + ((size_t)t * B + row) * H + j0;
+            const float* c1p = p.c_seq + ((size_t)(t + 1) * B + row) * H + j0;
+            cpv[0] = *reinterpret_cast<const float4*>(c0p); cpv[1] = *reinterpret_cast<const float4*>(c0p + 4);
+            cnv[0] = *reinterpret_cast<const float4*>(c1p); cnv[1] = *reinterpret_cast<const float4*>(c1p + 4);
+            if (t >= 2) {                                                      // saved activations come from HBM: pull t-2 into L2 early
+              prefetch_l2(ap - (size_t)2 * B * (4 * H));
+              prefetch_l2(c0p - (size_t)2 * B * H);
+              prefetch_l2(p.dh_seq + ((size_t)(t - 2) * B + row) * H + j0);
             }
           }
-          break;
-        }
-        uint32_t gpk[16];
+          if (s > 0) {
+            ok = wait_bar<false>(&ss->tmem_full[tile], tphase, abort_flag);
+            if (!ok) break;
+            tc::fence_after_sync();
+            if (dbg_thread && tile == 0) p.dbg[4 * s + 1] = gtime();
+            uint32_t v[32];
+            tc::tmem_ld32(taddr0 + tile * BN, v);
+            tc::tmem_ld_wait();
+            tc::fence_before_sync();
+            // reduce-scatter over the 4 K-quarters: column chunk q (16 wide, bf16) goes to member q's slot [ks] (DSMEM)
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const uint4 a4 = av[jj >> 1];
-          const uint32_t aa = (jj & 1) ? a4.z : a4.x, ab = (jj & 1) ? a4.w : a4.y;
-          const float ig = bf_lo(aa), fg = bf_hi(aa), gg = bf_lo(ab), og = bf_hi(ab);
-          const uint32_t dw = (jj >> 1) == 0 ? dhv.x : (jj >> 1) == 1 ? dhv.y : (jj >> 1) == 2 ? dhv.z : dhv.w;
-          const float dht = dh[jj] + ((jj & 1) ? bf_hi(dw) : bf_lo(dw));
-          const float cprev = reinterpret_cast<const float*>(cpv)[jj];
-          const float tcn = ts::tanhf_fast(reinterpret_cast<const float*>(cnv)[jj]);
-          const float dct = dc[jj] + dht * og * (1.f - tcn * tcn);
-          const float d_o = dht * tcn, d_i = dct * gg, d_f = dct * cprev, d_g = dct * ig;
-          dc[jj] = dct * fg;
-          gpk[2 * jj] = pack_bf2(d_i * ig * (1.f - ig), d_f * fg * (1.f - fg));
-          gpk[2 * jj + 1] = pack_bf2(d_g * (1.f - gg * gg), d_o * og * (1.f - og));
-        }
-        {
-          // next iteration's operand first: this thread's 32 gate columns = 4 chunks of row rloc of k-block j0/16
-          const size_t blk = ((size_t)t * p.tiles_m + mb) * (4 * H / BK) + (j0 / 16);
-          __nv_bfloat16* tp = p.a_tiled + blk * (BM * BK) + rloc * BK;
+            for (int qq = 0; qq < 2; ++qq) {
+              const uint32_t dst = mapa(xbase + (uint32_t)((ks * BM + rloc) * 32), (uint32_t)(2 * half + qq));
+              uint32_t pk[8];
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            stg16(tp + (((4 * half + i) ^ (rloc & 7)) * 8), make_uint4(gpk[4 * i], gpk[4 * i + 1], gpk[4 * i + 2], gpk[4 * i + 3]));
-        }
-        epi_bar();
-        if (etid == 0) {
-          signal();
-          if (dbg_thread) p.dbg[4 * s + 2] = gtime();
-        }
-        if (valid) {                                   // the [T,B,4H] copy for the weight-gradient GEMMs: off the critical path
-          __nv_bfloat16* gp = p.dpre + ((size_t)t * B + row) * (4 * H) + 4 * j0;
+              for (int i = 0; i < 8; ++i) pk[i] = pack_bf2(__uint_as_float(v[16 * qq + 2 * i]), __uint_as_float(v[16 * qq + 2 * i + 1]));
+              st_cluster_u4(dst, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+              st_cluster_u4(dst + 16, make_uint4(pk[4], pk[5], pk[6], pk[7]));
+            }
+            epi_bar();
+            if (etid < 4) mbar_arrive_remote(mapa(xbar, (uint32_t)etid));
+            ok = wait_bar<true>(&ss->xchg_full[tile], xphase, abort_flag);
+            if (!ok) break;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) stg16(gp + 8 * i, make_uint4(gpk[4 * i], gpk[4 * i + 1], gpk[4 * i + 2], gpk[4 * i + 3]));
+            for (int i = 0; i < 8; ++i) dh[tile][i] = 0.f;
+#pragma unroll
+            for (int src = 0; src < 4; ++src) {
+              const uint4 x4 = *reinterpret_cast<const uint4*>(xbuf + (size_t)(src * BM + rloc) * 32 + 16 * half);
+              const uint32_t w[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { dh[tile][2 * i] += bf_lo(w[i]); dh[tile][2 * i + 1] += bf_hi(w[i]); }
+            }
+          }
+          if (s == p.T) {
+            if (valid) {
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                *reinterpret_cast<float4*>(p.dh0 + (size_t)row * H + j0 + 4 * i) = make_float4(dh[tile][4 * i], dh[tile][4 * i + 1], dh[tile][4 * i + 2], dh[tile][4 * i + 3]);
+                *reinterpret_cast<float4*>(p.dc0 + (size_t)row * H + j0 + 4 * i) = make_float4(dc[tile][4 * i], dc[tile][4 * i + 1], dc[tile][4 * i + 2], dc[tile][4 * i + 3]);
+              }
+            }
+            continue;
+          }
+          uint32_t gpk[16];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const uint4 a4 = av[jj >> 1];
+            const uint32_t aa = (jj & 1) ? a4.z : a4.x, ab = (jj & 1) ? a4.w : a4.y;
+            const float ig = bf_lo(aa), fg = bf_hi(aa), gg = bf_lo(ab), og = bf_hi(ab);
+            const uint32_t dw = (jj >> 1) == 0 ? dhv.x : (jj >> 1) == 1 ? dhv.y : (jj >> 1) == 2 ? dhv.z : dhv.w;
+            const float dht = dh[tile][jj] + ((jj & 1) ? bf_hi(dw) : bf_lo(dw));
+            const float cprev = reinterpret_cast<const float*>(cpv)[jj];
+            const float tcn = ts::tanhf_fast(reinterpret_cast<const float*>(cnv)[jj]);
+            const float dct = dc[tile][jj] + dht * og * (1.f - tcn * tcn);
+            const float d_o = dht * tcn, d_i = dct * gg, d_f = dct * cprev, d_g = dct * ig;
+            dc[tile][jj] = dct * fg;
+            gpk[2 * jj] = pack_bf2(d_i * ig * (1.f - ig), d_f * fg * (1.f - fg));
+            gpk[2 * jj + 1] = pack_bf2(d_g * (1.f - gg * gg), d_o * og * (1.f - og));
+          }
+          {
+            // next iteration's operand first: this thread's 32 gate columns = 4 chunks of row rloc of k-block j0/16
+            const size_t blk = ((size_t)t * p.tiles_m + mb) * (4 * H / BK) + (j0 / 16);
+            __nv_bfloat16* tp = p.a_tiled + blk * (BM * BK) + rloc * BK;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              stg16(tp + (((4 * half + i) ^ (rloc & 7)) * 8), make_uint4(gpk[4 * i], gpk[4 * i + 1], gpk[4 * i + 2], gpk[4 * i + 3]));
+          }
+          epi_bar();
+          if (etid == 0) {
+            signal_counter(p.sync + mb);
+            if (dbg_thread && tile == 0) p.dbg[4 * s + 2] = gtime();
+          }
+          if (valid) {                                   // the [T,B,4H] copy for the weight-gradient GEMMs: off the critical path
+            __nv_bfloat16* gp = p.dpre + ((size_t)t * B + row) * (4 * H) + 4 * j0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) stg16(gp + 8 * i, make_uint4(gpk[4 * i], gpk[4 * i + 1], gpk[4 * i + 2], gpk[4 * i + 3]));
+          }
         }
+        if (s > 0) { tphase ^= 1; xphase ^= 1; }
       }
     }
   }
@@ -553,7 +577,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
   __syncthreads();
   if (kBwd) cluster_sync_all();                  // nobody exits while a peer may still write into / arrive on its smem
   if (threadIdx.x == 0 && ss->abort_flag) atomicExch(reinterpret_cast<int*>(p.sync + 63), 1);
-  if (warp == 2) tc::tmem_dealloc(tmem_d, 64);
+  if (warp == 2) tc::tmem_dealloc(tmem_d, kTmemCols);
 }
 
 // One small launch instead of ~12 framework ops: h_seq[0] <- h0, c_seq[0] <- c0, the swizzled tile image of h0 (slot 0
@@ -579,14 +603,14 @@ __global__ void seq_prologue_kernel(const __nv_bfloat16* __restrict__ h0, const 
   if (blockIdx.x == 0 && threadIdx.x < 16) sync[threadIdx.x] = 0u;
 }
 
-size_t smem_bytes(int H, bool bwd, int stages) {
-  return (size_t)(H / BK) * kWBlockBytes + (size_t)stages * kABytes + (bwd ? kXchgBytes : 0) + sizeof(SeqSmem) + 1024;
+size_t smem_bytes(int H, bool bwd, int stages, int tiles) {
+  return (size_t)(H / BK) * kWBlockBytes + (size_t)stages * kABytes + (bwd ? tiles * kXchgBytes : 0) + sizeof(SeqSmem) + 1024;
 }
 
-template <bool kBwd, int kStages>
+template <bool kBwd, int kStages, int kTiles>
 int launch_cfg(const CUtensorMap& tw, const SeqParams& p, int grid, cudaStream_t st) {
-  auto kern = lstm_seq_kernel<kBwd, kStages>;
-  const size_t smem = smem_bytes(p.H, kBwd, kStages);
+  auto kern = lstm_seq_kernel<kBwd, kStages, kTiles>;
+  const size_t smem = smem_bytes(p.H, kBwd, kStages, kTiles);
   if (smem > 227 * 1024) return -4;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
@@ -607,47 +631,58 @@ int launch_cfg(const CUtensorMap& tw, const SeqParams& p, int grid, cudaStream_t
 }
 
 template <bool kBwd>
-int dispatch(const CUtensorMap& tw, const SeqParams& p, int grid, int stages, cudaStream_t st) {
-  switch (stages) {
-    case 2: return launch_cfg<kBwd, 2>(tw, p, grid, st);
-    case 3: return launch_cfg<kBwd, 3>(tw, p, grid, st);
-    case 4: return launch_cfg<kBwd, 4>(tw, p, grid, st);
-    case 5: return launch_cfg<kBwd, 5>(tw, p, grid, st);
-    case 6: return launch_cfg<kBwd, 6>(tw, p, grid, st);
+int dispatch(const CUtensorMap& tw, const SeqParams& p, int grid, int stages, int tiles, cudaStream_t st) {
+  if (tiles == 2) {
+    switch (stages) {
+      case 2: return launch_cfg<kBwd, 2, 2>(tw, p, grid, st);
+      case 3: return launch_cfg<kBwd, 3, 2>(tw, p, grid, st);
+      case 4: return launch_cfg<kBwd, 4, 2>(tw, p, grid, st);
+      case 5: return launch_cfg<kBwd, 5, 2>(tw, p, grid, st);
+      case 6: return launch_cfg<kBwd, 6, 2>(tw, p, grid, st);
+    }
+  } else {
+    switch (stages) {
+      case 2: return launch_cfg<kBwd, 2, 1>(tw, p, grid, st);
+      case 3: return launch_cfg<kBwd, 3, 1>(tw, p, grid, st);
+      case 4: return launch_cfg<kBwd, 4, 1>(tw, p, grid, st);
+      case 5: return launch_cfg<kBwd, 5, 1>(tw, p, grid, st);
+      case 6: return launch_cfg<kBwd, 6, 1>(tw, p, grid, st);
+    }
   }
   return -5;
 }
 
-int pick_stages(int H, bool bwd) {
+int pick_stages(int H, bool bwd, int tiles) {
   for (int s = 6; s >= 2; --s)
-    if (smem_bytes(H, bwd, s) <= 227 * 1024) return s;
+    if (smem_bytes(H, bwd, s, tiles) <= 227 * 1024) return s;
   return 0;
 }
 
 }  // namespace
 
 // sync_ws: >= 64 u32; [0..tiles_m) step counters (zeroed by the caller before every launch), [63] sticky error flag.
-// variant (tuning knob, 0 = defaults) = 16*stages + 4096*debug_mode:  stages 0 -> deepest ring that fits next to the
-// resident weight slice.
+// variant (tuning knob, 0 = defaults) = tiles_per_cta + 16*stages + 4096*debug_mode:  tiles_per_cta 0 -> 1 (set 2 to let a
+// CTA alternate two batch tiles);  stages 0 -> deepest ring that fits next to the resident weight slice.
 template <bool kBwd>
 static int seq_common(SeqParams& p, const void* w_base, int variant, cudaStream_t st) {
   const int H = p.H, B = p.B;
   if (H % 64 != 0) { ts::set_last_error("lstm_seq: H must be a multiple of 64"); return -2; }
   const int tiles_m = (B + BM - 1) / BM, tiles_n = kBwd ? (H / BN) * 4 : 4 * H / BN;
-  int stages = (variant >> 4) & 15;
+  int stages = (variant >> 4) & 15, tiles = variant & 15;
   p.debug_mode = (variant >> 12) & 3;
+  if (tiles != 2 || tiles_m % 2 != 0) tiles = 1;
   int dev = 0;
   cudaGetDevice(&dev);
-  const int grid = tiles_m * tiles_n;
+  const int grid = (tiles_m / tiles) * tiles_n;
   if (grid > ts::sm_count(dev)) { ts::set_last_error("lstm_seq: grid exceeds SM count (not co-resident)"); return -3; }
-  if (stages == 0) stages = pick_stages(H, kBwd);
-  if (stages < 2 || smem_bytes(H, kBwd, stages) > 227 * 1024) { ts::set_last_error("lstm_seq: weight slice does not fit in shared memory"); return -4; }
+  if (stages == 0) stages = pick_stages(H, kBwd, tiles);
+  if (stages < 2 || smem_bytes(H, kBwd, stages, tiles) > 227 * 1024) { ts::set_last_error("lstm_seq: weight slice does not fit in shared memory"); return -4; }
   const int K = kBwd ? 4 * H : H, N = kBwd ? H : 4 * H;
   CUtensorMap tw;
   if (int rc = ts::make_tmap_2d_bf16(&tw, w_base, (uint64_t)N, (uint64_t)K, (uint64_t)K, BK, BN)) return rc;
   p.tiles_n = tiles_n;
   p.tiles_m = tiles_m;
-  int rc = dispatch<kBwd>(tw, p, grid, stages, st);
+  int rc = dispatch<kBwd>(tw, p, grid, stages, tiles, st);
   if (rc == -21) ts::set_last_error("lstm_seq_bwd: clusters of 4 are not co-resident on this device");
   return rc;
 }

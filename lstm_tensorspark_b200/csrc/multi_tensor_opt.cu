@@ -15,10 +15,19 @@ TS_DEVICE uint2 pack_bf16x4(float4 v) {
   return r;
 }
 
+// step_dev != null: lr_t is derived in-kernel from the device-resident step counter (bumped by inc_step_kernel right
+// before), so a CUDA-graph replay of the training step applies the correct Adam bias correction every time.
+__global__ void inc_step_kernel(int* step) { *step += 1; }
+
 __global__ void __launch_bounds__(256) flat_adam_kernel(float4* __restrict__ p, const float4* __restrict__ g,
                                                         float4* __restrict__ m, float4* __restrict__ v,
                                                         uint2* __restrict__ shadow, size_t n4, float lr_t, float b1,
-                                                        float b2, float eps, float wd, float gscale) {
+                                                        float b2, float eps, float wd, float gscale,
+                                                        const int* __restrict__ step_dev) {
+  if (step_dev != nullptr) {
+    const float t = (float)(*step_dev);
+    lr_t = lr_t * sqrtf(1.f - powf(b2, t)) / (1.f - powf(b1, t));      // lr_t arrives as the base learning rate
+  }
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 pv = p[i], gv = g[i], mv = m[i], vv = v[i];
@@ -65,11 +74,12 @@ int grid_for(size_t n4) {
 }  // namespace
 
 extern "C" int ts_flat_adam(float* p, const float* g, float* m, float* v, void* shadow, long long n, float lr_t,
-                            float b1, float b2, float eps, float wd, float gscale, cudaStream_t st) {
+                            float b1, float b2, float eps, float wd, float gscale, cudaStream_t st, int* step_dev) {
   if (n % 4) return -2;
   size_t n4 = (size_t)n / 4;
+  if (step_dev) inc_step_kernel<<<1, 1, 0, st>>>(step_dev);
   flat_adam_kernel<<<grid_for(n4), 256, 0, st>>>((float4*)p, (const float4*)g, (float4*)m, (float4*)v, (uint2*)shadow,
-                                                 n4, lr_t, b1, b2, eps, wd, gscale);
+                                                 n4, lr_t, b1, b2, eps, wd, gscale, step_dev);
   return (int)cudaGetLastError();
 }
 

@@ -79,6 +79,7 @@ class TrainEngine:
         sx.copy_(x, non_blocking=True)
         sy.copy_(y, non_blocking=True)
         self._graph.replay()
+        self.optimizer.step_count += 1          # host mirror; the kernels use the device-resident counter
         return sloss
 
     def maybe_average(self, force: bool = False):
@@ -91,8 +92,8 @@ class TrainEngine:
 
     # ---------------------------------------------------------------------------------------------------
     def capture(self, x: torch.Tensor, y: torch.Tensor, warmup: int = 3):
-        """Capture fwd+bwd+update into one CUDA graph (static shapes).  Adam's bias-corrected lr is a host scalar
-        baked at capture time, so graphs are only used with SGD or after the correction has saturated."""
+        """Capture fwd+bwd+update into one CUDA graph (static shapes).  Adam's bias correction is derived in-kernel from
+        a device-resident step counter, so replays are exact."""
         assert self.device.type == "cuda"
         sx, sy = x.clone(), y.clone()
         s = torch.cuda.Stream()

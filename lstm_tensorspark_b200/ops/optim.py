@@ -25,6 +25,9 @@ class FlatOptimizer:
         self.kind = kind
         self.lr, self.beta1, self.beta2, self.eps, self.weight_decay = lr, beta1, beta2, eps, weight_decay
         self.step_count = 0
+        # device-resident mirror of step_count: the Adam kernels derive the bias correction from it, so a captured
+        # CUDA graph of the training step stays exact across replays
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=flat.data.device) if flat.data.is_cuda else None
         if kind == "adam":
             self.m = torch.zeros_like(flat.data)
             self.v = torch.zeros_like(flat.data)
@@ -67,6 +70,8 @@ class FlatOptimizer:
 
     def load_state_dict(self, sd):
         self.step_count = int(sd["step"])
+        if self.step_dev is not None:
+            self.step_dev.fill_(self.step_count)
         if self.m is not None and sd.get("m") is not None:
             self.m.copy_(sd["m"].to(self.m.device))
             self.v.copy_(sd["v"].to(self.v.device))

@@ -58,6 +58,10 @@ class Communicator:
     def broadcast_params_(self, flat: FlatParams, src: int = 0):
         pass
 
+    def optimizer_state(self, optimizer) -> dict:
+        """Checkpointable optimizer state (complete on every rank)."""
+        return optimizer.state_dict()
+
     def close(self):
         pass
 

@@ -22,8 +22,9 @@ from ..ops.cuda_ext import ext
 from .comm import TorchDistComm
 
 MODE_AVG, MODE_SGD, MODE_ADAM = 0, 1, 2
-TWO_SHOT_BYTES = int(os.environ.get("LSTM_TS_AR_TWO_SHOT_BYTES", str(256 * 1024)))
+TWO_SHOT_BYTES = int(os.environ.get("LSTM_TS_AR_TWO_SHOT_BYTES", str(32 * 1024)))     # measured: two-shot wins from ~16 KB up (profiles/)
 AR_BLOCKS = int(os.environ.get("LSTM_TS_AR_BLOCKS", "64"))
+AR_BLOCKS_LARGE = int(os.environ.get("LSTM_TS_AR_BLOCKS_LARGE", "128"))   # messages >= 32 MB
 
 
 def _align(x: int, a: int = 4096) -> int:
@@ -57,7 +58,11 @@ class SymmetricArena:
         off = self.off
         assert off + nbytes <= self.nbytes, "symmetric arena exhausted"
         self.off = _align(off + nbytes)
-        t = self.buf[off:off + nbytes].view(dtype)
+        # NOT a view of self.buf: views share one autograd version counter, and an in-place update of the grad region
+        # would then invalidate bf16-shadow views saved for backward.  set_() aliases the storage with its own counter.
+        esize = torch.empty((), dtype=dtype).element_size()
+        t = torch.empty(0, dtype=dtype, device=self.buf.device).set_(
+            self.buf.untyped_storage(), (self.buf.storage_offset() + off) // esize, (numel,))
         return t, off
 
     def peers(self, off: int):
@@ -113,7 +118,7 @@ class FusedComm(TorchDistComm):
         return bool(self.arena.mc_base)
 
     def _launch(self, mode: int, off_in: int, n: int, lr: float = 0.0, b1: float = 0.0, b2: float = 0.0, eps: float = 0.0,
-                wd: float = 0.0, m=None, v=None, force: Optional[str] = None):
+                wd: float = 0.0, m=None, v=None, force: Optional[str] = None, step_dev=None):
         E = ext()
         A = self.arena
         two_shot = (4 * n >= TWO_SHOT_BYTES) if force is None else (force == "two_shot")
@@ -125,7 +130,8 @@ class FusedComm(TorchDistComm):
         ptrs = self._ptr_table(off_in_eff)
         E.fused_allreduce(ptrs, A.mc(off_in_eff) if mc else 0, A.mc(self.off_data) if mc else 0,
                           A.mc(self.off_shadow) if mc else 0, m, v, self.epochs, self.err, n, self.rank, self.world_size,
-                          mode, two_shot, mc, AR_BLOCKS, lr, b1, b2, eps, wd, float(self.timeout_s))
+                          mode, two_shot, mc, AR_BLOCKS_LARGE if 4 * n >= (32 << 20) else AR_BLOCKS, lr, b1, b2, eps, wd,
+                          float(self.timeout_s), step_dev)
         self.launches += 1
 
     # ------------------------------------------------------------------------------------------------
@@ -138,10 +144,23 @@ class FusedComm(TorchDistComm):
         optimizer.step_count += 1
         n = flat.padded_numel
         if optimizer.kind == "adam":
-            self._launch(MODE_ADAM, self.off_grad, n, optimizer.bias_corrected_lr(), optimizer.beta1, optimizer.beta2,
-                         optimizer.eps, optimizer.weight_decay, optimizer.m, optimizer.v, force=force)
+            self._launch(MODE_ADAM, self.off_grad, n, optimizer.lr, optimizer.beta1, optimizer.beta2,
+                         optimizer.eps, optimizer.weight_decay, optimizer.m, optimizer.v, force=force,
+                         step_dev=optimizer.step_dev)
         else:
             self._launch(MODE_SGD, self.off_grad, n, optimizer.lr, wd=optimizer.weight_decay, force=force)
+
+    def optimizer_state(self, optimizer) -> dict:
+        """Two-shot gradient sync keeps Adam's (m, v) for 1/N of the elements on each rank (the slice it reduces and
+        updates); the other entries stay zero, so a SUM across ranks reassembles the full state for a checkpoint."""
+        sd = optimizer.state_dict()
+        n = self.flat.padded_numel
+        if optimizer.kind == "adam" and self.world_size > 1 and 4 * n >= TWO_SHOT_BYTES and optimizer.step_count > 0:
+            for k in ("m", "v"):
+                full = getattr(optimizer, k).detach().clone()
+                dist.all_reduce(full, op=dist.ReduceOp.SUM)
+                sd[k] = full.cpu()
+        return sd
 
     def check_errors(self):
         if int(self.err.item()) != 0:

@@ -99,21 +99,11 @@ def train_rnn(partition, cfg: Config, rank: int = 0, world_size: int = 1, comm: 
                                            in_features=cfg.in_features)
     batch_size = D.resolve_batch_size(cfg.batch_size, train_x.shape[0])
 
-    # ---- model -------------------------------------------------------------------------------------
-    clear_weight_decay_collection()
-    seed = cfg.seed + (1000003 * (rank + 1) if cfg.independent_init else 0)
-    gen = torch.Generator(device="cpu")
-    gen.manual_seed(seed)
-    model = SequenceClassifier(cfg, batch_size=batch_size, device="cpu", generator=gen)
-    model.to(device)
-    model.build_flat()
-    comm.adopt(model.flat)
-    model.set_compute_dtype(dtype)
-    make_opt = train_optimizer(cfg.learning_rate) if train_optimizer is not None else None
-    if make_opt is not None:
-        optimizer = make_opt(model.flat)
-    else:
-        optimizer = FlatOptimizer(model.flat, cfg.learning_rate, cfg.optimizer)
+    # ---- model + optimizer + sync = one TrainEngine (the same object bench.py drives) ----------------------
+    from .engine import TrainEngine
+    eng = TrainEngine(cfg, rank, world_size, comm, batch_size=batch_size, device=device, dtype=dtype,
+                      train_optimizer=train_optimizer)
+    model, optimizer = eng.model, eng.optimizer
 
     # ---- run directory -----------------------------------------------------------------
     current_exec = run_stamp or str(time.time())
@@ -170,23 +160,14 @@ def train_rnn(partition, cfg: Config, rank: int = 0, world_size: int = 1, comm: 
             os._exit(17)
         train_input, train_labels = loader.next()
 
-        with M.nvtx_range("fwd_bwd", cfg.nvtx):
-            model.flat.zero_grad()
-            loss, _logits, _correct = model(train_input, train_labels)
-            if cfg.weight_decay:
-                from .models.recurrent.lstm import weight_decay_terms
-                loss = loss + torch.stack(weight_decay_terms()).sum()
-            loss.backward()
-        with M.nvtx_range("update", cfg.nvtx):
-            if cfg.sync_mode == "grad_allreduce" and world_size > 1:
-                comm.grad_step_(model.flat, optimizer)
-            else:
-                optimizer.step()
+        with M.nvtx_range("step", cfg.nvtx):
+            if cfg.cuda_graph and device.type == "cuda" and eng._graph is None and step == start_step + 3:
+                eng.capture(train_input, train_labels)          # static shapes: replay the captured step from here on
+            loss = eng.step(train_input, train_labels)
         samples += batch_size
 
-        if cfg.sync_mode == "param_avg" and cfg.sync_every and world_size > 1 and (step + 1) % cfg.sync_every == 0:
-            with M.nvtx_range("param_avg", cfg.nvtx):
-                comm.average_params_(model.flat, cfg.average_scope)
+        with M.nvtx_range("param_avg", cfg.nvtx):
+            eng.maybe_average()
 
         is_eval = (step % cfg.evaluate_every == 0) or (step + 1) == max_steps
         if use_bar or is_eval:
@@ -199,7 +180,7 @@ def train_rnn(partition, cfg: Config, rank: int = 0, world_size: int = 1, comm: 
                 saver.save(model.reference_state_dict(), global_step=step,
                            extra={"rank": rank, "world_size": world_size, "partition_key": partition_key,
                                   "loss": t_loss, "config": cfg.__dict__},
-                           opt_state={"optimizer": optimizer.state_dict(), "loader": loader.state_dict()})
+                           opt_state={"optimizer": comm.optimizer_state(optimizer), "loader": loader.state_dict()})
                 with torch.no_grad(), M.capture(sink):
                     h = model.features(train_input)      # same batch, from the initial state (src/rnn.py:276-279)
                     logits = model.head(h)
@@ -212,9 +193,8 @@ def train_rnn(partition, cfg: Config, rank: int = 0, world_size: int = 1, comm: 
                 total_steps.set_description("Loss: {:.4f} - t_acc {:.3f}".format(t_loss, t_acc))
 
     # ---- the cross-replica average (src/rnn.py:393-407) ------------------------------------------------
-    if world_size > 1 and cfg.sync_mode == "param_avg":
-        with M.nvtx_range("final_param_avg", cfg.nvtx):
-            comm.average_params_(model.flat, cfg.average_scope)
+    with M.nvtx_range("final_param_avg", cfg.nvtx):
+        eng.maybe_average(force=True)
     device_ms = timer.stop_ms()
     end_time = time.time() - start
     n_steps = max(1, max_steps - start_step)

@@ -37,7 +37,9 @@ def _worker(rank, world, n_elems):
         opt = FlatOptimizer(flat, 1e-2, "adam")
         p_ref = flat.data.clone(); m_ref = torch.zeros_like(p_ref); v_ref = torch.zeros_like(p_ref)
         for step in (1, 2):
-            gs = [torch.sin(torch.arange(n, dtype=torch.float32) * 0.01 * (r + 1) + step).to(dev) for r in range(world)]
+            # bounded away from zero: Adam's update is ill-conditioned where sum(g) ~ 0, and the in-switch (NVLS) summation
+            # order legitimately differs from the reference order
+            gs = [(1.0 + 0.5 * torch.sin(torch.arange(n, dtype=torch.float32) * 0.01 * (r + 1) + step)).to(dev) for r in range(world)]
             flat.grad.copy_(gs[rank])
             torch.cuda.synchronize(); dist.barrier(device_ids=[rank])
             comm.grad_step_(flat, opt, force=force)
