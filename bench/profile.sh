@@ -12,12 +12,12 @@ case "$what" in
   launches)
     ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $BENCH > gpurun_out/launches.out 2>&1 ;;
   seq)
-    ncu --set full --clock-control none --import-source on -k regex:lstm_seq_kernel -s 4 -c 2 -f -o gpurun_out/prof_seq $BENCH > gpurun_out/prof_seq.out 2>&1 ;;
+    ncu --set full --clock-control none --import-source on -k regex:lstm_seq_kernel -s 4 -c 4 -f -o gpurun_out/prof_seq $BENCH > gpurun_out/prof_seq.out 2>&1 ;;
   gemm)
     ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_tn_kernel -s 2 -c 1 -f -o gpurun_out/prof_gemm $BENCH > gpurun_out/prof_gemm.out 2>&1 ;;
   sanitize)
     for tool in memcheck racecheck synccheck; do
-      compute-sanitizer --tool $tool python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "pointwise or head or adam or tcgen05_gemm or persistent" > gpurun_out/sanitizer_$tool.log 2>&1
+      compute-sanitizer --tool $tool python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "pointwise or head_xent or adam or (tcgen05_gemm and 128-128-64) or (persistent and 3-128-64-64) or generic_shape" > gpurun_out/sanitizer_$tool.log 2>&1
       tail -3 gpurun_out/sanitizer_$tool.log
     done ;;
 esac
