@@ -310,32 +310,35 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
         const long long tw0 = prof ? clock64() : 0;
 #pragma unroll
         for (int i = 0; i < kGroup; ++i) rdy[i] = (i < g) ? tc::mbar_try_wait_u32(full0 + 8 * st[i], ph[i]) : true;
-#pragma unroll
-        for (int i = 0; i < kGroup; ++i)
-          if (ok && !rdy[i]) ok = wait_bar<false>(&ss->full[st[i]], ph[i], abort_flag);
-        if (!ok) break;
         if (prof) { const long long tw1 = clock64(); if (kb == 0 && tile == 0) t_first = tw1 - tw0; else t_wait += tw1 - tw0; }
-        tc::fence_after_sync();
-        if (tc::elect_one()) {
+        // the group's try_waits were issued together (their latencies overlap); each k-block's MMAs go out as soon as ITS
+        // stage has landed, so a late stage does not hold back the ones in front of it
 #pragma unroll
-          for (int i = 0; i < kGroup; ++i) {
-            if (i < g) {
-              if (p.debug_mode == 2) {
-                tc::mbar_arrive(&ss->empty[st[i]]);
-              } else {
-                const uint64_t da = desc_a0 + (uint64_t)(st[i] * (kABytes >> 4));
-                const uint64_t dbi = db + (uint64_t)(i * (kWBlockBytes >> 4));
-                if (kb == 0 && i == 0) tc::mma_bf16_ss_first(acc, da, dbi, idesc); else tc::mma_bf16_ss_acc(acc, da, dbi, idesc);
-                tc::mma_bf16_ss_acc(acc, da + 2, dbi + 2, idesc);
-                tc::mma_bf16_ss_acc(acc, da + 4, dbi + 4, idesc);
-                tc::mma_bf16_ss_acc(acc, da + 6, dbi + 6, idesc);
-                tc::mma_commit_u32(empty0 + 8 * st[i]);
+        for (int i = 0; i < kGroup; ++i) {
+          if (i < g && ok) {
+            if (!rdy[i]) ok = wait_bar<false>(&ss->full[st[i]], ph[i], abort_flag);
+            if (ok) {
+              tc::fence_after_sync();
+              if (tc::elect_one()) {
+                if (p.debug_mode == 2) {
+                  tc::mbar_arrive(&ss->empty[st[i]]);
+                  if (kb + i + 1 >= num_kb) tc::mbar_arrive(&ss->tmem_full[tile]);
+                } else {
+                  const uint64_t da = desc_a0 + (uint64_t)(st[i] * (kABytes >> 4));
+                  const uint64_t dbi = db + (uint64_t)(i * (kWBlockBytes >> 4));
+                  if (kb == 0 && i == 0) tc::mma_bf16_ss_first(acc, da, dbi, idesc); else tc::mma_bf16_ss_acc(acc, da, dbi, idesc);
+                  tc::mma_bf16_ss_acc(acc, da + 2, dbi + 2, idesc);
+                  tc::mma_bf16_ss_acc(acc, da + 4, dbi + 4, idesc);
+                  tc::mma_bf16_ss_acc(acc, da + 6, dbi + 6, idesc);
+                  tc::mma_commit_u32(empty0 + 8 * st[i]);
+                  if (kb + i + 1 >= num_kb) tc::mma_commit_u32(tfull);
+                }
               }
+              __syncwarp();
             }
           }
-          if (kb + g >= num_kb) { if (p.debug_mode == 2) tc::mbar_arrive(&ss->tmem_full[tile]); else tc::mma_commit_u32(tfull); }
         }
-        __syncwarp();
+        if (!ok) break;
         db += (uint64_t)(g * (kWBlockBytes >> 4));
 #pragma unroll
         for (int i = 0; i < kGroup; ++i)

@@ -117,3 +117,12 @@ def test_device_shard_and_pinned_loader_cpu():
     pl = D.PinnedHostLoader(x, y, 8, "cpu", shuffle=False)
     xb2, yb2 = pl.next()
     assert np.allclose(xb2.numpy(), x[:8]) and pl.bytes_per_batch == 8 * 5 * 3 * 4 + 64
+
+
+def test_pinned_loader_yields_batches_in_order_cpu():
+    x = np.arange(40 * 3, dtype=np.float32).reshape(40, 3)
+    y = np.arange(40, dtype=np.int64)
+    pl = D.PinnedHostLoader(x, y, 8, "cpu", shuffle=False)
+    seen = [pl.next()[1].clone().numpy() for _ in range(7)]       # crosses an epoch boundary (5 batches per pass)
+    assert [int(b[0]) for b in seen] == [0, 8, 16, 24, 32, 0, 8]
+    assert all(len(b) == 8 for b in seen)
