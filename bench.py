@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--seq_len", type=int, default=MODEL["seq_len"])
     ap.add_argument("--batch_size", type=int, default=MODEL["batch_size"])
     ap.add_argument("--no_e2e", action="store_true")
+    ap.add_argument("--config", type=int, default=3, choices=[3, 4],
+                    help="BASELINE.json config: 3 = 2x1024 T=128 B=256 per-step grad allreduce (headline); "
+                         "4 = 4x2048 T=512 B=64 per-epoch parameter average (one average inside the timed region)")
     return ap.parse_args()
 
 
@@ -155,6 +158,8 @@ def timed_loop(torch, dist, world, device, step_fn, steps, warmup, clocks=None):
 
 def main():
     args = parse()
+    if args.config == 4:
+        args.hidden_units, args.in_features, args.seq_len, args.batch_size = "2048,2048,2048,2048", 2048, 512, 64
     if args.impl == "reference":
         return run_reference(args)
     import torch
@@ -188,7 +193,8 @@ def main():
         from lstm_tensorspark_b200.ops import cuda_lstm
         comm_kind = args.comm if args.comm != "auto" else "fused"
         cfg = Config(hidden_units=args.hidden_units, in_features=D, seq_len=T, batch_size=B, num_classes=C,
-                     partitions=world, sync_mode="grad_allreduce", optimizer=args.optimizer, init="scaled",
+                     partitions=world, sync_mode="grad_allreduce" if args.config == 3 else "param_avg",
+                     sync_every=0 if args.config == 3 else args.steps, average_scope="all", optimizer=args.optimizer, init="scaled",
                      learn_initial_state=False, comm=comm_kind, dtype="bf16", device="cuda", learning_rate=1e-3, quiet=True)
         comm = make_communicator(comm_kind if world > 1 else "auto", rank, world, device)
         eng = TrainEngine(cfg, rank, world, comm, batch_size=B, device=device, dtype=torch.bfloat16)
@@ -202,7 +208,9 @@ def main():
         def step_dev():
             i = it["i"] % nb
             it["i"] += 1
-            return eng.step(dev_x[i * B:(i + 1) * B], dev_y[i * B:(i + 1) * B])
+            loss = eng.step(dev_x[i * B:(i + 1) * B], dev_y[i * B:(i + 1) * B])
+            eng.maybe_average()                       # config 4: the per-epoch parameter average (every `steps` steps)
+            return loss
 
         loader = Dm.PinnedHostLoader(xs, ys, B, device, dtype=torch.bfloat16, shuffle=False, seed=rank)
         loss_host = torch.empty((), dtype=torch.float32, pin_memory=True)
@@ -210,6 +218,7 @@ def main():
         def step_e2e():
             x, y = loader.next()                       # pinned host -> device copy of this step's inputs
             loss = eng.step(x, y)
+            eng.maybe_average()
             loss_host.copy_(loss.float(), non_blocking=False)    # device -> host read of the result
             return loss_host
 
@@ -246,7 +255,7 @@ def main():
            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "impl": args.impl,
            "config": {"model": model_name, "global_batch": B * n_gpus, "per_gpu_batch": B, "seq_len": T, "in_features": D,
-                      "num_classes": C, "parallelism": par, "sync": "per-step gradient allreduce" if n_gpus > 1 else "none",
+                      "num_classes": C, "parallelism": par, "sync": ("per-step gradient allreduce" if args.config == 3 else "per-epoch parameter average") if n_gpus > 1 else "none",
                       "l2": "per-step working set (activations+inputs, >1 GB) exceeds the 126 MB L2; 4 rotating input batches",
                       **cfg_extra},
            "clocks": clk, "gpu_launches": launches * args.steps}

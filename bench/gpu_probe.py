@@ -288,6 +288,12 @@ def check_umma():
             _emit("umma", mode=mode, M=M, N=N, cycles_per_mma=float(out[0]) / float(out[1]), cycles_per_group_of_4=4 * float(out[0]) / float(out[1]))
 
 
+def check_seq_h2048():
+    """Streamed-weights variant (BASELINE.json config 4 shape: H = 2048, B = 64)."""
+    _seq_case(6, 64, 2048, 256, check_bwd=True, time_it=True)
+    _seq_case(32, 64, 2048, 2048, check_bwd=False, time_it=True)
+
+
 def check_generic():
     os.environ["LSTM_TS_FORCE_GENERIC"] = "1"
     from lstm_tensorspark_b200.ops import cuda_lstm
@@ -311,7 +317,7 @@ def check_iris_gpu():
     _emit("iris_gpu_standalone", rc=r.returncode, tail=(r.stdout + r.stderr)[-600:])
 
 
-CHECKS = {"skew": check_skew, "seq_tiles": check_seq_tiles, "umma": check_umma, "seq_tune": check_seq_tune, "env": check_env, "simple": check_simple, "gemm": check_gemm, "generic": check_generic, "seq_small": check_seq_small,
+CHECKS = {"seq_h2048": check_seq_h2048, "skew": check_skew, "seq_tiles": check_seq_tiles, "umma": check_umma, "seq_tune": check_seq_tune, "env": check_env, "simple": check_simple, "gemm": check_gemm, "generic": check_generic, "seq_small": check_seq_small,
           "seq_big": check_seq_big, "engine": check_engine, "iris_gpu": check_iris_gpu}
 
 

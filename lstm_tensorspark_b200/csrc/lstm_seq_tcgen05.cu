@@ -37,7 +37,7 @@ constexpr int BM = 128;           // batch rows per CTA (UMMA M)
 constexpr int BN = 64;            // accumulator columns per CTA (UMMA N)
 constexpr int BK = 64;            // K per pipeline stage (one 128 B swizzle atom of bf16)
 constexpr int UK = 16;            // UMMA K
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 9;
 constexpr int kEpiWarp0 = 4;
 constexpr int kABytes = BM * BK * 2;          // 16 KB
 constexpr int kWBlockBytes = BN * BK * 2;     // 8 KB per 64-wide K block
@@ -175,15 +175,18 @@ struct SeqParams {
 // kTiles = 2: the CTA alternates TWO independent 128-row batch tiles (same resident weight slice): while one tile sits
 // in its epilogue + grid barrier (latency), the other one streams its operand and runs its MMAs.  Half as many CTAs are
 // needed (64 for B = 256, H = 1024), which leaves SMs free for the weight-gradient GEMMs that run concurrently.
-template <bool kBwd, int kStages, int kTiles>
+// kStream = true (H too large for a resident slice, e.g. H = 2048: W_h alone is 32 MB): the weight k-block travels through
+// the ring next to its operand k-block (24 KB stages, W comes out of L2 every step); everything else is unchanged.
+template <bool kBwd, int kStages, int kTiles, bool kStream>
 __global__ void __launch_bounds__(384, 1)
 lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int num_kb = p.H / BK;
-  uint8_t* smem_w = smem;                                    // resident weight slice: num_kb blocks of [64 x 64]
-  uint8_t* smem_a = smem + (size_t)num_kb * kWBlockBytes;    // kStages x 16 KB
-  uint8_t* smem_x = smem_a + kStages * kABytes;              // backward: DSMEM exchange buffer (bf16)
+  constexpr int kStageBytes = kStream ? kABytes + kWBlockBytes : kABytes;
+  uint8_t* smem_w = smem;                                    // resident weight slice: num_kb blocks of [64 x 64] (not kStream)
+  uint8_t* smem_a = smem + (kStream ? 0 : (size_t)num_kb * kWBlockBytes);    // kStages x (16 KB [+ 8 KB weight block])
+  uint8_t* smem_x = smem_a + kStages * kStageBytes;          // backward: DSMEM exchange buffer (bf16)
   SeqSmem* ss = reinterpret_cast<SeqSmem*>(smem_x + (kBwd ? kTiles * kXchgBytes : 0));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -216,7 +219,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
   if (warp == 0) {
     // ======================================================================== producer
     const uint32_t w_bar = tc::smem_u32(&ss->w_full);
-    if (tc::elect_one()) {
+    if (!kStream && tc::elect_one()) {
       tc::mbar_expect_tx_u32(w_bar, (uint32_t)(num_kb * kWBlockBytes));
       // forward: rows = gate columns [64 nb, +64) of W_h [4H, H].  backward: rows = hidden columns [64 nb, +64) of
       // W_h^T [H, 4H], K offset = quarter ks.
@@ -230,16 +233,22 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
     bool ok = true;
     // one k-block: the operand is a contiguous 16 KB block = the 128B-swizzled K-major [128 x 64] tile image written by
     // the epilogues (no tensor map, no coordinates)
+    const int wc0 = kBwd ? ks * p.H : 0, wc1 = nb * BN;       // weight tensor-map coordinates of this CTA's slice
+    int kb_cur = 0;                                           // k-block index of the next load within the step (kStream)
+    auto issue = [&](uint32_t st_, const __nv_bfloat16* src) {   // elected lane: fill ring stage st_ with one k-block
+      const uint32_t fb = full0 + 8 * st_;
+      if (p.debug_mode == 1) { tc::mbar_arrive(&ss->full[st_]); return; }
+      tc::mbar_expect_tx_u32(fb, kStageBytes);
+      tc::bulk_load_1d_u32(a0 + st_ * kStageBytes, src, kABytes, fb);
+      if (kStream) tc::tma_load_2d_u32(a0 + st_ * kStageBytes + kABytes, &tmap_w, fb, wc0 + kb_cur * BK, wc1);
+    };
     auto load_block = [&](const __nv_bfloat16* src) -> bool {
       if (!tc::mbar_try_wait_u32(empty0 + 8 * stage, phase ^ 1)) {
         if (!wait_bar<false>(&ss->empty[stage], phase ^ 1, abort_flag)) return false;
       }
-      if (tc::elect_one()) {
-        const uint32_t fb = full0 + 8 * stage;
-        if (p.debug_mode == 1) tc::mbar_arrive(&ss->full[stage]);
-        else { tc::mbar_expect_tx_u32(fb, kABytes); tc::bulk_load_1d_u32(a0 + stage * kABytes, src, kABytes, fb); }
-      }
+      if (tc::elect_one()) issue(stage, src);
       __syncwarp();
+      ++kb_cur;
       if (++stage == kStages) { stage = 0; phase ^= 1; }
       return true;
     };
@@ -252,16 +261,13 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
       if (!r0 && !wait_bar<false>(&ss->empty[stage], phase ^ 1, abort_flag)) return false;
       if (!r1 && !wait_bar<false>(&ss->empty[s1], ph1 ^ 1, abort_flag)) return false;
       if (tc::elect_one()) {
-        const uint32_t fb0 = full0 + 8 * stage, fb1 = full0 + 8 * s1;
-        if (p.debug_mode == 1) { tc::mbar_arrive(&ss->full[stage]); tc::mbar_arrive(&ss->full[s1]); }
-        else {
-          tc::mbar_expect_tx_u32(fb0, kABytes);
-          tc::bulk_load_1d_u32(a0 + stage * kABytes, src, kABytes, fb0);
-          tc::mbar_expect_tx_u32(fb1, kABytes);
-          tc::bulk_load_1d_u32(a0 + s1 * kABytes, src + BM * BK, kABytes, fb1);
-        }
+        issue(stage, src);
+        ++kb_cur;
+        issue(s1, src + BM * BK);
+        --kb_cur;
       }
       __syncwarp();
+      kb_cur += 2;
       stage = s1 + 1; phase = ph1;
       if (stage == kStages) { stage = 0; phase ^= 1; }
       return true;
@@ -274,6 +280,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
         asm volatile("fence.proxy.async.global;" ::: "memory");
         if (p.dbg && blockIdx.x == 0 && lane == 0 && tile == 0) p.dbg[4 * s + 0] = gtime();
         const __nv_bfloat16* src = p.a_tiled + (((size_t)tsl * p.tiles_m + mb) * nkb_all + (kBwd ? ks * num_kb : 0)) * (BM * BK);
+        kb_cur = 0;
         for (int pr = 0; pr < pairs && ok; ++pr, src += 2 * BM * BK) ok = load_pair(src);
         if (odd && ok) ok = load_block(src);
       }
@@ -281,7 +288,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
   } else if (warp == 1) {
     // ======================================================================== MMA issuer
     constexpr uint32_t idesc = tc::make_idesc_bf16_f32(BM, BN);
-    bool ok = wait_bar<false>(&ss->w_full, 0, abort_flag);
+    bool ok = kStream ? true : wait_bar<false>(&ss->w_full, 0, abort_flag);
     const uint32_t full0 = tc::smem_u32(&ss->full[0]), empty0 = tc::smem_u32(&ss->empty[0]);
     const uint32_t tfull0 = tc::smem_u32(&ss->tmem_full[0]);
     const uint64_t desc_a0 = tc::desc_kmajor_sw128(tc::smem_u32(smem_a));      // + stage * (kABytes >> 4)
@@ -310,34 +317,34 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
         const long long tw0 = prof ? clock64() : 0;
 #pragma unroll
         for (int i = 0; i < kGroup; ++i) rdy[i] = (i < g) ? tc::mbar_try_wait_u32(full0 + 8 * st[i], ph[i]) : true;
-        if (prof) { const long long tw1 = clock64(); if (kb == 0 && tile == 0) t_first = tw1 - tw0; else t_wait += tw1 - tw0; }
-        // the group's try_waits were issued together (their latencies overlap); each k-block's MMAs go out as soon as ITS
-        // stage has landed, so a late stage does not hold back the ones in front of it
 #pragma unroll
-        for (int i = 0; i < kGroup; ++i) {
-          if (i < g && ok) {
-            if (!rdy[i]) ok = wait_bar<false>(&ss->full[st[i]], ph[i], abort_flag);
-            if (ok) {
-              tc::fence_after_sync();
-              if (tc::elect_one()) {
-                if (p.debug_mode == 2) {
-                  tc::mbar_arrive(&ss->empty[st[i]]);
-                  if (kb + i + 1 >= num_kb) tc::mbar_arrive(&ss->tmem_full[tile]);
-                } else {
-                  const uint64_t da = desc_a0 + (uint64_t)(st[i] * (kABytes >> 4));
-                  const uint64_t dbi = db + (uint64_t)(i * (kWBlockBytes >> 4));
-                  if (kb == 0 && i == 0) tc::mma_bf16_ss_first(acc, da, dbi, idesc); else tc::mma_bf16_ss_acc(acc, da, dbi, idesc);
-                  tc::mma_bf16_ss_acc(acc, da + 2, dbi + 2, idesc);
-                  tc::mma_bf16_ss_acc(acc, da + 4, dbi + 4, idesc);
-                  tc::mma_bf16_ss_acc(acc, da + 6, dbi + 6, idesc);
-                  tc::mma_commit_u32(empty0 + 8 * st[i]);
-                  if (kb + i + 1 >= num_kb) tc::mma_commit_u32(tfull);
-                }
+        for (int i = 0; i < kGroup; ++i)
+          if (ok && !rdy[i]) ok = wait_bar<false>(&ss->full[st[i]], ph[i], abort_flag);
+        if (!ok) break;
+        if (prof) { const long long tw1 = clock64(); if (kb == 0 && tile == 0) t_first = tw1 - tw0; else t_wait += tw1 - tw0; }
+        // all stages of the group have landed: issue its 4*g MMAs back to back (measured faster than issuing each
+        // k-block as soon as its own stage lands: one fence + one elect per turn instead of per k-block)
+        tc::fence_after_sync();
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int i = 0; i < kGroup; ++i) {
+            if (i < g) {
+              if (p.debug_mode == 2) {
+                tc::mbar_arrive(&ss->empty[st[i]]);
+              } else {
+                const uint64_t da = desc_a0 + (uint64_t)(st[i] * (kStageBytes >> 4));
+                const uint64_t dbi = kStream ? da + (uint64_t)(kABytes >> 4) : db + (uint64_t)(i * (kWBlockBytes >> 4));
+                if (kb == 0 && i == 0) tc::mma_bf16_ss_first(acc, da, dbi, idesc); else tc::mma_bf16_ss_acc(acc, da, dbi, idesc);
+                tc::mma_bf16_ss_acc(acc, da + 2, dbi + 2, idesc);
+                tc::mma_bf16_ss_acc(acc, da + 4, dbi + 4, idesc);
+                tc::mma_bf16_ss_acc(acc, da + 6, dbi + 6, idesc);
+                tc::mma_commit_u32(empty0 + 8 * st[i]);
               }
-              __syncwarp();
             }
           }
+          if (kb + g >= num_kb) { if (p.debug_mode == 2) tc::mbar_arrive(&ss->tmem_full[tile]); else tc::mma_commit_u32(tfull); }
         }
+        __syncwarp();
         if (!ok) break;
         db += (uint64_t)(g * (kWBlockBytes >> 4));
 #pragma unroll
@@ -606,14 +613,15 @@ __global__ void seq_prologue_kernel(const __nv_bfloat16* __restrict__ h0, const 
   if (blockIdx.x == 0 && threadIdx.x < 16) sync[threadIdx.x] = 0u;
 }
 
-size_t smem_bytes(int H, bool bwd, int stages, int tiles) {
-  return (size_t)(H / BK) * kWBlockBytes + (size_t)stages * kABytes + (bwd ? tiles * kXchgBytes : 0) + sizeof(SeqSmem) + 1024;
+size_t smem_bytes(int H, bool bwd, int stages, int tiles, bool stream = false) {
+  const size_t ring = (size_t)stages * (stream ? kABytes + kWBlockBytes : kABytes);
+  return (stream ? 0 : (size_t)(H / BK) * kWBlockBytes) + ring + (bwd ? tiles * kXchgBytes : 0) + sizeof(SeqSmem) + 1024;
 }
 
-template <bool kBwd, int kStages, int kTiles>
+template <bool kBwd, int kStages, int kTiles, bool kStream = false>
 int launch_cfg(const CUtensorMap& tw, const SeqParams& p, int grid, cudaStream_t st) {
-  auto kern = lstm_seq_kernel<kBwd, kStages, kTiles>;
-  const size_t smem = smem_bytes(p.H, kBwd, kStages, kTiles);
+  auto kern = lstm_seq_kernel<kBwd, kStages, kTiles, kStream>;
+  const size_t smem = smem_bytes(p.H, kBwd, kStages, kTiles, kStream);
   if (smem > 227 * 1024) return -4;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
@@ -634,7 +642,15 @@ int launch_cfg(const CUtensorMap& tw, const SeqParams& p, int grid, cudaStream_t
 }
 
 template <bool kBwd>
-int dispatch(const CUtensorMap& tw, const SeqParams& p, int grid, int stages, int tiles, cudaStream_t st) {
+int dispatch(const CUtensorMap& tw, const SeqParams& p, int grid, int stages, int tiles, bool stream, cudaStream_t st) {
+  if (stream) {                                    // streamed weights: 24 KB stages, one batch tile per CTA
+    switch (stages) {
+      case 4: return launch_cfg<kBwd, 4, 1, true>(tw, p, grid, st);
+      case 6: return launch_cfg<kBwd, 6, 1, true>(tw, p, grid, st);
+      case 8: return launch_cfg<kBwd, 8, 1, true>(tw, p, grid, st);
+    }
+    return -5;
+  }
   if (tiles == 2) {
     switch (stages) {
       case 2: return launch_cfg<kBwd, 2, 2>(tw, p, grid, st);
@@ -674,18 +690,25 @@ static int seq_common(SeqParams& p, const void* w_base, int variant, cudaStream_
   int stages = (variant >> 4) & 15, tiles = variant & 15;
   p.debug_mode = (variant >> 12) & 3;
   if (tiles != 2 || tiles_m % 2 != 0) tiles = 1;
+  // resident weight slice if it fits next to >= 4 ring stages, else stream the weights through the ring
+  const bool stream = smem_bytes(H, kBwd, 4, 1) > 227 * 1024 || ((variant >> 8) & 1);
+  if (stream) tiles = 1;
   int dev = 0;
   cudaGetDevice(&dev);
   const int grid = (tiles_m / tiles) * tiles_n;
   if (grid > ts::sm_count(dev)) { ts::set_last_error("lstm_seq: grid exceeds SM count (not co-resident)"); return -3; }
-  if (stages == 0) stages = pick_stages(H, kBwd, tiles);
-  if (stages < 2 || smem_bytes(H, kBwd, stages, tiles) > 227 * 1024) { ts::set_last_error("lstm_seq: weight slice does not fit in shared memory"); return -4; }
+  if (stream) {
+    if (stages != 4 && stages != 6 && stages != 8) stages = smem_bytes(H, kBwd, 8, 1, true) <= 227 * 1024 ? 8 : 6;
+  } else {
+    if (stages == 0) stages = pick_stages(H, kBwd, tiles);
+    if (stages < 2 || smem_bytes(H, kBwd, stages, tiles) > 227 * 1024) { ts::set_last_error("lstm_seq: weight slice does not fit in shared memory"); return -4; }
+  }
   const int K = kBwd ? 4 * H : H, N = kBwd ? H : 4 * H;
   CUtensorMap tw;
   if (int rc = ts::make_tmap_2d_bf16(&tw, w_base, (uint64_t)N, (uint64_t)K, (uint64_t)K, BK, BN)) return rc;
   p.tiles_n = tiles_n;
   p.tiles_m = tiles_m;
-  int rc = dispatch<kBwd>(tw, p, grid, stages, tiles, st);
+  int rc = dispatch<kBwd>(tw, p, grid, stages, tiles, stream, st);
   if (rc == -21) ts::set_last_error("lstm_seq_bwd: clusters of 4 are not co-resident on this device");
   return rc;
 }

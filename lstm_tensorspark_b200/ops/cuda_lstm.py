@@ -90,10 +90,9 @@ def fast_path_supported(B: int, H: int, dtype: torch.dtype, device) -> bool:
     if FORCE_GENERIC or dtype != torch.bfloat16 or H % 64 != 0:
         return False
     tiles_m = (B + 127) // 128
-    if tiles_m * (H // 16) > _sms(device):
-        return False
-    smem = H * 64 * 2 + 2 * 16384 + 16384 + 2048      # resident slice + >=2 stages + DSMEM exchange (+ barriers)
-    return smem <= 227 * 1024 and tiles_m <= 16
+    # one CTA per (batch tile, 64 gate columns); all of them must be co-resident (grid barrier).  The weight slice stays in
+    # shared memory when it fits (H <= 1024), larger H streams it through the ring (csrc/lstm_seq_tcgen05.cu, kStream)
+    return tiles_m * (H // 16) <= _sms(device) and tiles_m <= 16
 
 
 def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
