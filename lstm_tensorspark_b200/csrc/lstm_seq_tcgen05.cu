@@ -235,11 +235,12 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
     // the epilogues (no tensor map, no coordinates)
     const int wc0 = kBwd ? ks * p.H : 0, wc1 = nb * BN;       // weight tensor-map coordinates of this CTA's slice
     int kb_cur = 0;                                           // k-block index of the next load within the step (kStream)
+    uint32_t a_bytes = kABytes;                               // a partial batch tile only needs its first rows (8-row swizzle atoms)
     auto issue = [&](uint32_t st_, const __nv_bfloat16* src) {   // elected lane: fill ring stage st_ with one k-block
       const uint32_t fb = full0 + 8 * st_;
       if (p.debug_mode == 1) { tc::mbar_arrive(&ss->full[st_]); return; }
-      tc::mbar_expect_tx_u32(fb, kStageBytes);
-      tc::bulk_load_1d_u32(a0 + st_ * kStageBytes, src, kABytes, fb);
+      tc::mbar_expect_tx_u32(fb, a_bytes + (kStream ? kWBlockBytes : 0));
+      tc::bulk_load_1d_u32(a0 + st_ * kStageBytes, src, a_bytes, fb);
       if (kStream) tc::tma_load_2d_u32(a0 + st_ * kStageBytes + kABytes, &tmap_w, fb, wc0 + kb_cur * BK, wc1);
     };
     auto load_block = [&](const __nv_bfloat16* src) -> bool {
@@ -281,6 +282,10 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
         if (p.dbg && blockIdx.x == 0 && lane == 0 && tile == 0) p.dbg[4 * s + 0] = gtime();
         const __nv_bfloat16* src = p.a_tiled + (((size_t)tsl * p.tiles_m + mb) * nkb_all + (kBwd ? ks * num_kb : 0)) * (BM * BK);
         kb_cur = 0;
+        {
+          const int rows = p.B - mb * BM;                     // rows beyond B are never read back from the accumulator
+          a_bytes = rows >= BM ? kABytes : (uint32_t)(((rows + 7) / 8) * 8 * BK * 2);
+        }
         for (int pr = 0; pr < pairs && ok; ++pr, src += 2 * BM * BK) ok = load_pair(src);
         if (odd && ok) ok = load_block(src);
       }
