@@ -69,6 +69,17 @@ class ReplicaResult(dict):
     pass
 
 
+def _check_device_errors(device: torch.device, comm) -> None:
+    """Failure surfacing: the persistent LSTM kernels and the fused allreduce bound every in-kernel wait and
+    raise a sticky device flag instead of hanging; turn it into a Python error at the sync points we have anyway."""
+    if device.type != "cuda":
+        return
+    from .ops import cuda_lstm
+    cuda_lstm.check_kernel_errors(device)
+    if hasattr(comm, "check_errors"):
+        comm.check_errors()
+
+
 def train_rnn(partition, cfg: Config, rank: int = 0, world_size: int = 1, comm: Optional[Communicator] = None,
               train_optimizer: Optional[Callable] = None, standalone: bool = False,
               run_stamp: Optional[str] = None) -> Optional[ReplicaResult]:
@@ -176,6 +187,7 @@ def train_rnn(partition, cfg: Config, rank: int = 0, world_size: int = 1, comm: 
             total_steps.set_description("Loss: {:.4f} - t_acc {:.3f}".format(t_loss, t_acc))
 
         if is_eval:
+            _check_device_errors(device, comm)       # sticky in-kernel timeout flags (dead peer / stalled grid barrier)
             with M.nvtx_range("eval_ckpt", cfg.nvtx):
                 saver.save(model.reference_state_dict(), global_step=step,
                            extra={"rank": rank, "world_size": world_size, "partition_key": partition_key,
