@@ -45,6 +45,7 @@ def main():
     from lstm_tensorspark_b200.models.flat import FlatParams
     from lstm_tensorspark_b200.parallel.fused_comm import FusedComm
     max_bytes = int(os.environ.get("SWEEP_MAX_BYTES", str(1 << 30)))
+    tune = os.environ.get("SWEEP_TUNE", "0") == "1"          # also sweep grid size / unroll of the NVLS kernel
     comm = FusedComm(rank, world, dev, 120)
     p = torch.nn.Parameter(torch.zeros(max_bytes // 4, device=dev))
     flat = FlatParams([p], [])
@@ -57,13 +58,19 @@ def main():
         n = max(4096 // 4, (n + 3) // 4 * 4)
         iters = 200 if size <= (1 << 20) else (50 if size <= (1 << 26) else 10)
         rec = {"bytes": n * 4, "world": world}
-        variants = [("one_shot", "one_shot", "0"), ("two_shot_p2p", "two_shot", "0")]
+        variants = [("one_shot", "one_shot", "0", 0, False), ("two_shot_p2p", "two_shot", "0", 0, False)]
         if comm.arena.mc_base:
-            variants.append(("two_shot_nvls", "two_shot", "auto"))
-        for name, force, mc in variants:
+            variants.append(("two_shot_nvls", "two_shot", "auto", 0, False))
+            if tune and size >= (1 << 22):
+                variants += [("nvls_b64", "two_shot", "auto", 64, False), ("nvls_b64_u4", "two_shot", "auto", 64, True),
+                             ("nvls_b128", "two_shot", "auto", 128, False), ("nvls_b128_u4", "two_shot", "auto", 128, True),
+                             ("nvls_b256", "two_shot", "auto", 256, False)]
+        for name, force, mc, blocks, unroll in variants:
             if force == "one_shot" and size > (1 << 26):
                 continue
             comm.use_multicast = mc
+            comm.blocks_override = blocks
+            comm.mc_unroll = unroll
 
             def fn():
                 comm._launch(0, comm.off_data, n, force=force)

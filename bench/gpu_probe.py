@@ -181,15 +181,15 @@ def check_seq_tune():
     from lstm_tensorspark_b200.ops.cuda_ext import ext
     E = ext()
     dev = torch.device("cuda")
-    for (T, B, H) in ((32, 256, 1024),):
+    for (T, B, H) in ((128, 256, 1024),):
         torch.manual_seed(0)
         gx = (torch.randn(T, B, 4 * H, device=dev) * 0.5).bfloat16()
         whb = (torch.randn(4 * H, H, device=dev) / H ** 0.5).bfloat16()
         bias = torch.zeros(4 * H, device=dev)
         h0 = torch.zeros(B, H, device=dev).bfloat16(); c0 = torch.zeros(B, H, device=dev)
         ws = cuda_lstm._sync_ws(dev)
-        for (tiles, st, mode) in ((1, 0, 0), (2, 0, 0), (2, 4, 0)):
-            v = tiles + 16 * st + 4096 * mode
+        for (tiles, st, mode, sync, acq, nosplit) in ((1, 0, 0, 1, 0, 1), (1, 0, 0, 0, 0, 1), (1, 0, 0, 1, 0, 0), (1, 0, 0, 0, 0, 0), (1, 4, 0, 0, 0, 0), (1, 0, 5, 0, 0, 0)):
+            v = tiles + 16 * st + 4096 * mode + 65536 * sync + 262144 * acq + 524288 * nosplit
             try:
                 ms = _time_ms(lambda: E.lstm_seq_fwd(gx, whb, bias, h0, c0, ws, v), iters=5, warm=2)
                 dbg = torch.zeros(4 * (T + 2) + 64, dtype=torch.int64, device=dev)
@@ -209,7 +209,7 @@ def check_seq_tune():
                 mma_total = [(int(x) >> 40) & 0xFFFFF for x in w3]
                 e = dbg[4 * (T + 2):4 * (T + 2) + 3].cpu()
                 acc8, sig8 = int(d[0, 1]), int(d[0, 2])
-                _emit("fwd_variant", T=T, B=B, H=H, tiles=tiles, stages=st, debug_mode=mode, us_per_step=ms * 1e3 / T,
+                _emit("fwd_variant", T=T, B=B, H=H, tiles=tiles, stages=st, debug_mode=mode, sync=sync, acq=acq, nosplit=nosplit, us_per_step=ms * 1e3 / T,
                       mma_first_wait_cyc=sum(mma_first) / 16, mma_later_wait_cyc=sum(mma_wait) / 16, mma_step_cyc=sum(mma_total) / 16,
                       epi_ld_ns=int(e[0]) - acc8, epi_math_store_ns=int(e[1]) - int(e[0]), epi_bar_ns=int(e[2]) - int(e[1]), epi_signal_ns=sig8 - int(e[2]),
                       load_mma_us=float((accum - waited).float().mean()) / 1e3, epi_us=float((sig - accum).float().mean()) / 1e3,

@@ -25,7 +25,7 @@
 namespace {
 
 constexpr int kMaxRanks = 16;
-constexpr int kMaxBlocks = 128;
+constexpr int kMaxBlocks = 256;
 constexpr int kThreads = 512;
 
 enum Mode { MODE_AVG = 0, MODE_SGD = 1, MODE_ADAM = 2 };
@@ -145,7 +145,7 @@ TS_DEVICE float effective_lr(const ARArgs& a) {
 }
 __global__ void ar_inc_step_kernel(int* step) { *step += 1; }
 
-template <int kMode, bool kMulticast>
+template <int kMode, bool kMulticast, bool kUnroll = false>
 __global__ void __launch_bounds__(kThreads) ar_two_shot_kernel(const __grid_constant__ ARArgs a) {
   const float lr = kMode == MODE_ADAM ? effective_lr(a) : a.lr;
   uint32_t epoch = a.epochs[blockIdx.x];
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kThreads) ar_two_shot_kernel(const __grid_cons
   long long lo = per * a.rank, hi = lo + per < a.n4 ? lo + per : a.n4;
   long long stride = (long long)gridDim.x * kThreads;
   long long i = lo + (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (kMulticast) {
+  if (kMulticast && kUnroll) {
     // 4 independent switch reductions in flight per thread (NVLink round trips are ~2 us: memory-level parallelism,
     // not thread count, sets the bandwidth of the large-message regime)
     for (; i + 3 * stride < hi; i += 4 * stride) {
@@ -244,7 +244,8 @@ __global__ void __launch_bounds__(kThreads) ar_one_shot_kernel(const __grid_cons
 template <int kMode>
 int launch_mode(const ARArgs& a, int two_shot, int multicast, int blocks, cudaStream_t st) {
   if (two_shot) {
-    if (multicast) ar_two_shot_kernel<kMode, true><<<blocks, kThreads, 0, st>>>(a);
+    if (multicast == 2) ar_two_shot_kernel<kMode, true, true><<<blocks, kThreads, 0, st>>>(a);   // 4 switch reductions in flight per thread
+    else if (multicast) ar_two_shot_kernel<kMode, true><<<blocks, kThreads, 0, st>>>(a);
     else ar_two_shot_kernel<kMode, false><<<blocks, kThreads, 0, st>>>(a);
   } else {
     ar_one_shot_kernel<kMode><<<blocks, kThreads, 0, st>>>(a);

@@ -44,14 +44,24 @@ constexpr int kWBlockBytes = BN * BK * 2;     // 8 KB per 64-wide K block
 constexpr int kXchgBytes = 4 * BM * 16 * 2;   // backward: 4 source slots of [128 x 16] bf16 partial chunks
 constexpr long long kSpinLimit = 6000000000LL;   // ~3 s of SM clocks: a bug surfaces as an error, not a hung GPU
 
+// sync workspace (u32 words): [0,16) grid-barrier counters, [64,320) per-CTA step flags, [512 + 32 i) k-block arrival
+// counters (one 128 B line each, i < tiles_m * 4H/64 <= 148 + ...), [kSyncWords-1] sticky error flag
+constexpr int kSyncWords = 8192;
+constexpr int kSyncErr = kSyncWords - 1;
+constexpr int kSyncFlags = 64;
+constexpr int kSyncKb = 512;
+
 struct SeqSmem {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
   uint64_t w_full;
   uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];       // epilogue -> MMA issuer: the accumulator has been read (8 warp arrivals)
   uint64_t xchg_full[2];
+  uint64_t xchg_free[2];        // every cluster member has consumed its exchange buffer of the previous step (4 remote arrivals)
   uint32_t tmem_slot;
   int abort_flag;
+  uint32_t kb_idx[kMaxStages];  // which k-block sits in ring stage s (the producer fills stages in ARRIVAL order)
   float bias[64];
 };
 
@@ -71,8 +81,20 @@ TC_DEVICE void st_cluster_f4(uint32_t addr, float4 v) {
 TC_DEVICE void st_cluster_u4(uint32_t addr, uint4 v) {
   asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// 16 B into a cluster member's shared memory; the bytes are accounted on ITS mbarrier (complete_tx), so the receiver needs
+// no release/acquire round trip: it arms the barrier with expect_tx and waits, exactly as for a TMA load.
+TC_DEVICE void st_async_u4(uint32_t remote_addr, uint4 v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];"
+               ::"r"(remote_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(remote_bar) : "memory");
+}
 TC_DEVICE void mbar_arrive_remote(uint32_t remote_bar_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
+}
+// "Buffer consumed" notifications carry no data: the reads they order were complete (their values used) before the CTA
+// barrier that precedes the arrive.  The .release form compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR - a second
+// GPU-scope fence per step that competes with the one the dataflow signal needs.
+TC_DEVICE void mbar_arrive_remote_relaxed(uint32_t remote_bar_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
 }
 TC_DEVICE bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -121,6 +143,24 @@ TC_DEVICE bool wait_counter(const unsigned int* ctr, unsigned int target, volati
     }
   }
 }
+TC_DEVICE unsigned int ld_acquire_gpu(const unsigned int* ctr) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+  return v;
+}
+TC_DEVICE uint2 ld_relaxed_gpu_v2(const unsigned int* ctr) {
+  uint2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(ctr) : "memory");
+  return v;
+}
+TC_DEVICE void st_release_gpu(unsigned int* ctr, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ctr), "r"(v) : "memory");
+}
+TC_DEVICE unsigned int ld_relaxed_gpu(const unsigned int* ctr) {      // coalesces across lanes (a divergent ld.acquire does not)
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+  return v;
+}
 TC_DEVICE void signal_counter(unsigned int* ctr) {
   asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
 }
@@ -130,6 +170,18 @@ TC_DEVICE uint4 ldg_nc16(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
+}
+// 256-bit accesses (sm_100 LDG/STG.256): half as many L2 requests as 16 B ones and only whole 32 B sectors - the
+// bookkeeping stores of a step are ~460 K requests chip-wide, and it is their COUNT that slows the operand stream down.
+struct alignas(32) U8 { uint32_t v[8]; };
+TC_DEVICE U8 ldg_nc32(const void* p) {
+  U8 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
+  return r;
+}
+TC_DEVICE void stg32(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f, uint32_t g, uint32_t h) {
+  asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h) : "memory");
 }
 TC_DEVICE void stg16(void* p, uint4 v) {
   asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -156,11 +208,13 @@ struct SeqParams {
   float* dc0;                  // [B,H] in: dL/dc_T, out: dL/dc_0
   __nv_bfloat16* a_tiled;      // streamed operand as pre-swizzled SMEM images: [time][tiles_m][K/64][128 rows][64] (16 KB blocks)
   int tiles_m;
-  int debug_mode;              // timing experiments only: 1 = skip operand loads, 2 = skip MMAs (results are garbage)
-  unsigned int* sync;          // [tiles_m] step counters; [63] error flag
+  int debug_mode;              // timing experiments only: 1 = skip operand loads, 2 = skip MMAs, 4 = half-size loads (garbage results), 3 = in-order stream
+  unsigned int* sync;          // [63] error flag; [64 + mb * nkb + kb] arrival counter of operand k-block kb of batch tile mb
   unsigned long long* dbg;     // optional [steps][4] timestamps of CTA 0 (ns)
   int T, B, H;
   int tiles_n;                 // CTAs per batch tile
+  int sync_mode;               // 0 = k-block arrival counters (dataflow), 1 = one counter per batch tile (grid barrier), 2 = per-CTA flags
+  int poll_acquire;            // experiment: ld.acquire polls instead of relaxed
 };
 
 // Work decomposition
@@ -177,24 +231,34 @@ struct SeqParams {
 // needed (64 for B = 256, H = 1024), which leaves SMs free for the weight-gradient GEMMs that run concurrently.
 // kStream = true (H too large for a resident slice, e.g. H = 2048: W_h alone is 32 MB): the weight k-block travels through
 // the ring next to its operand k-block (24 KB stages, W comes out of L2 every step); everything else is unchanged.
-template <bool kBwd, int kStages, int kTiles, bool kStream>
+// kFSplit (forward): a cluster of 2 CTAs splits K.  Each member contracts over HALF of h_{t-1} (8 instead of 16 operand
+// k-blocks per step at H = 1024: the ring then holds most of the step's operand at once - the stream is bound by bytes in
+// flight / L2 latency, not by bandwidth) against a [128 x H/2] weight slice (N = 128: 64 instead of 48 tensor-pipe cycles per
+// K = 16, but half as many instructions), and the two partial [128 x 128] accumulators are reduce-scattered through DSMEM:
+// every member ends up with the same 64 gate columns = 16 hidden units it owns in the unsplit kernel.
+template <bool kBwd, int kStages, int kTiles, bool kStream, bool kFSplit = false>
 __global__ void __launch_bounds__(384, 1)
 lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
+  static_assert(!(kFSplit && (kBwd || kStream || kTiles != 1)), "forward K-split: one tile, resident weights");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int num_kb = p.H / BK;
+  constexpr int kSplit = kBwd ? 4 : (kFSplit ? 2 : 1);       // cluster size = K-split factor
+  constexpr bool kCluster = kSplit > 1;
+  constexpr int kBNm = kFSplit ? 2 * BN : BN;                // accumulator columns per CTA (UMMA N)
+  constexpr int kWBlk = kBNm * BK * 2;                       // bytes of one resident weight k-block
+  const int num_kb = kFSplit ? p.H / (2 * BK) : p.H / BK;    // operand k-blocks this CTA contracts over per step
   constexpr int kStageBytes = kStream ? kABytes + kWBlockBytes : kABytes;
-  uint8_t* smem_w = smem;                                    // resident weight slice: num_kb blocks of [64 x 64] (not kStream)
-  uint8_t* smem_a = smem + (kStream ? 0 : (size_t)num_kb * kWBlockBytes);    // kStages x (16 KB [+ 8 KB weight block])
-  uint8_t* smem_x = smem_a + kStages * kStageBytes;          // backward: DSMEM exchange buffer (bf16)
-  SeqSmem* ss = reinterpret_cast<SeqSmem*>(smem_x + (kBwd ? kTiles * kXchgBytes : 0));
+  uint8_t* smem_w = smem;                                    // resident weight slice: num_kb blocks of [kBNm x 64] (not kStream)
+  uint8_t* smem_a = smem + (kStream ? 0 : (size_t)num_kb * kWBlk);    // kStages x (16 KB [+ 8 KB weight block])
+  uint8_t* smem_x = smem_a + kStages * kStageBytes;          // DSMEM exchange buffer (bf16 partial sums)
+  SeqSmem* ss = reinterpret_cast<SeqSmem*>(smem_x + (kCluster ? kTiles * kXchgBytes : 0));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mb0 = (blockIdx.x / p.tiles_n) * kTiles;          // first batch tile of this CTA
   const int in_mb = blockIdx.x % p.tiles_n;
-  const uint32_t crank = kBwd ? cluster_ctarank() : 0;
-  const int nb = kBwd ? in_mb / 4 : in_mb;
-  const int ks = kBwd ? (int)crank : 0;
+  const uint32_t crank = kCluster ? cluster_ctarank() : 0;
+  const int nb = in_mb / kSplit;                              // weight-row block of the cluster (64 rows; kFSplit: 128 rows)
+  const int ks = (int)crank;                                  // K-split member
   volatile int* abort_flag = &ss->abort_flag;
   const int steps = kBwd ? p.T + 1 : p.T;                    // backward runs one extra GEMM to produce dh_0
 
@@ -203,58 +267,62 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
     tc::prefetch_tmap(&tmap_w);
     for (int s = 0; s < kStages; ++s) { tc::mbar_init(&ss->full[s], 1); tc::mbar_init(&ss->empty[s], 1); }
     tc::mbar_init(&ss->w_full, 1);
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&ss->tmem_full[i], 1); tc::mbar_init(&ss->xchg_full[i], 4); }
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&ss->tmem_full[i], 1); tc::mbar_init(&ss->tmem_empty[i], 8);
+      tc::mbar_init(&ss->xchg_full[i], 1);                   // armed locally (expect_tx = the whole 16 KB buffer), filled by st.async
+      tc::mbar_init(&ss->xchg_free[i], kFSplit ? 1 : 4);     // remote arrivals: every writer of this buffer's readers
+    }
+    if (kCluster)
+      for (int i = 0; i < kTiles; ++i) tc::mbar_expect_tx_u32(tc::smem_u32(&ss->xchg_full[i]), (uint32_t)kXchgBytes);
     tc::fence_barrier_init();
   }
-  if (!kBwd && threadIdx.x >= 64 && threadIdx.x < 128) ss->bias[threadIdx.x - 64] = p.bias[nb * BN + threadIdx.x - 64];
-  constexpr uint32_t kTmemCols = kTiles == 2 ? 128 : 64;
+  if (!kBwd && threadIdx.x >= 64 && threadIdx.x < 128) ss->bias[threadIdx.x - 64] = p.bias[in_mb * BN + threadIdx.x - 64];
+  constexpr uint32_t kTmemCols = (kTiles == 2 || kFSplit) ? 128 : 64;
   if (warp == 2) { tc::tmem_alloc(&ss->tmem_slot, kTmemCols); tc::tmem_relinquish(); }
   tc::fence_before_sync();
   __syncthreads();
-  if (kBwd) cluster_sync_all();                 // peers' mbarriers are initialised before anyone arrives remotely
+  if (kCluster) cluster_sync_all();             // peers' mbarriers are initialised before anyone arrives remotely
   tc::fence_after_sync();
   const uint32_t tmem_d = ss->tmem_slot;
-  const int pairs = num_kb >> 1, odd = num_kb & 1;
 
   if (warp == 0) {
     // ======================================================================== producer
     const uint32_t w_bar = tc::smem_u32(&ss->w_full);
     if (!kStream && tc::elect_one()) {
-      tc::mbar_expect_tx_u32(w_bar, (uint32_t)(num_kb * kWBlockBytes));
-      // forward: rows = gate columns [64 nb, +64) of W_h [4H, H].  backward: rows = hidden columns [64 nb, +64) of
-      // W_h^T [H, 4H], K offset = quarter ks.
+      tc::mbar_expect_tx_u32(w_bar, (uint32_t)(num_kb * kWBlk));
+      // forward: rows = gate columns [kBNm nb, +kBNm) of W_h [4H, H] (K-split: K offset = half ks).  backward: rows = hidden
+      // columns [64 nb, +64) of W_h^T [H, 4H], K offset = quarter ks.
       for (int kb = 0; kb < num_kb; ++kb)
-        tc::tma_load_2d_u32(tc::smem_u32(smem_w) + kb * kWBlockBytes, &tmap_w, w_bar, (kBwd ? ks * p.H : 0) + kb * BK, nb * BN);
+        tc::tma_load_2d_u32(tc::smem_u32(smem_w) + kb * kWBlk, &tmap_w, w_bar, ks * num_kb * BK + kb * BK, nb * kBNm);
     }
     __syncwarp();
     const uint32_t full0 = tc::smem_u32(&ss->full[0]), empty0 = tc::smem_u32(&ss->empty[0]), a0 = tc::smem_u32(smem_a);
-    const int nkb_all = (kBwd ? 4 : 1) * num_kb;
+    const int nkb_all = kSplit * num_kb;
     uint32_t stage = 0, phase = 0;
     bool ok = true;
     // one k-block: the operand is a contiguous 16 KB block = the 128B-swizzled K-major [128 x 64] tile image written by
     // the epilogues (no tensor map, no coordinates)
-    const int wc0 = kBwd ? ks * p.H : 0, wc1 = nb * BN;       // weight tensor-map coordinates of this CTA's slice
-    int kb_cur = 0;                                           // k-block index of the next load within the step (kStream)
+    const int wc0 = ks * num_kb * BK, wc1 = nb * kBNm;        // weight tensor-map coordinates of this CTA's slice
     uint32_t a_bytes = kABytes;                               // a partial batch tile only needs its first rows (8-row swizzle atoms)
-    auto issue = [&](uint32_t st_, const __nv_bfloat16* src) {   // elected lane: fill ring stage st_ with one k-block
+    auto issue = [&](uint32_t st_, const __nv_bfloat16* src, int kb) {   // elected lane: fill ring stage st_ with k-block kb
       const uint32_t fb = full0 + 8 * st_;
+      ss->kb_idx[st_] = (uint32_t)kb;                         // published by the release of the expect_tx arrive below
       if (p.debug_mode == 1) { tc::mbar_arrive(&ss->full[st_]); return; }
       tc::mbar_expect_tx_u32(fb, a_bytes + (kStream ? kWBlockBytes : 0));
-      tc::bulk_load_1d_u32(a0 + st_ * kStageBytes, src, a_bytes, fb);
-      if (kStream) tc::tma_load_2d_u32(a0 + st_ * kStageBytes + kABytes, &tmap_w, fb, wc0 + kb_cur * BK, wc1);
+      tc::bulk_load_1d_u32(a0 + st_ * kStageBytes, src + (size_t)kb * (BM * BK), a_bytes, fb);
+      if (kStream) tc::tma_load_2d_u32(a0 + st_ * kStageBytes + kABytes, &tmap_w, fb, wc0 + kb * BK, wc1);
     };
-    auto load_block = [&](const __nv_bfloat16* src) -> bool {
+    auto load_block = [&](const __nv_bfloat16* src, int kb) -> bool {
       if (!tc::mbar_try_wait_u32(empty0 + 8 * stage, phase ^ 1)) {
         if (!wait_bar<false>(&ss->empty[stage], phase ^ 1, abort_flag)) return false;
       }
-      if (tc::elect_one()) issue(stage, src);
+      if (tc::elect_one()) issue(stage, src, kb);
       __syncwarp();
-      ++kb_cur;
       if (++stage == kStages) { stage = 0; phase ^= 1; }
       return true;
     };
     // two k-blocks per turn (both empty-barrier try_waits in flight together, two copies issued back to back)
-    auto load_pair = [&](const __nv_bfloat16* src) -> bool {
+    auto load_pair = [&](const __nv_bfloat16* src, int kb_a, int kb_b) -> bool {
       uint32_t s1 = stage + 1, ph1 = phase;
       if (s1 == kStages) { s1 = 0; ph1 ^= 1; }
       const bool r0 = tc::mbar_try_wait_u32(empty0 + 8 * stage, phase ^ 1);
@@ -262,37 +330,104 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
       if (!r0 && !wait_bar<false>(&ss->empty[stage], phase ^ 1, abort_flag)) return false;
       if (!r1 && !wait_bar<false>(&ss->empty[s1], ph1 ^ 1, abort_flag)) return false;
       if (tc::elect_one()) {
-        issue(stage, src);
-        ++kb_cur;
-        issue(s1, src + BM * BK);
-        --kb_cur;
+        issue(stage, src, kb_a);
+        issue(s1, src, kb_b);
       }
       __syncwarp();
-      kb_cur += 2;
       stage = s1 + 1; phase = ph1;
       if (stage == kStages) { stage = 0; phase ^= 1; }
       return true;
     };
+    // Dataflow instead of a grid barrier: every operand k-block (64 columns of h_{t-1} / dG_{t+1}) has its own arrival
+    // counter; the 32 lanes poll all of them at once and the blocks are pulled into the ring in the order in which their
+    // producer CTAs finish, so the stream and the MMAs start under the stragglers' epilogues (accumulation order is free).
+    const unsigned int per_step = kBwd ? 1u : 4u;             // arrivals per k-block and step (bwd: 1 CTA, fwd: 4 CTAs x 16 hidden)
+    const uint64_t all_kb = num_kb >= 64 ? ~0ull : ((1ull << num_kb) - 1ull);
     for (int s = kBwd ? 1 : 0; s < steps && ok; ++s) {
       const int tsl = kBwd ? p.T - s : s;       // forward step s consumes h_seq[s]; backward iteration s consumes dG[T-s]
       for (int tile = 0; tile < kTiles && ok; ++tile) {
         const int mb = mb0 + tile;
-        if (s > 0) ok = wait_counter(p.sync + mb, (unsigned)s * p.tiles_n, abort_flag);
-        asm volatile("fence.proxy.async.global;" ::: "memory");
-        if (p.dbg && blockIdx.x == 0 && lane == 0 && tile == 0) p.dbg[4 * s + 0] = gtime();
-        const __nv_bfloat16* src = p.a_tiled + (((size_t)tsl * p.tiles_m + mb) * nkb_all + (kBwd ? ks * num_kb : 0)) * (BM * BK);
-        kb_cur = 0;
+        const int kb_base = ks * num_kb;
+        const __nv_bfloat16* src = p.a_tiled + (((size_t)tsl * p.tiles_m + mb) * nkb_all + kb_base) * (BM * BK);
+        const unsigned int* ctr = p.sync + kSyncKb + ((size_t)mb * nkb_all + kb_base) * 32;
+        const unsigned int target = (unsigned)s * per_step;
         {
           const int rows = p.B - mb * BM;                     // rows beyond B are never read back from the accumulator
           a_bytes = rows >= BM ? kABytes : (uint32_t)(((rows + 7) / 8) * 8 * BK * 2);
+          if (p.debug_mode == 4) a_bytes = kABytes / 2;       // experiment: half the operand traffic (results are garbage)
         }
-        for (int pr = 0; pr < pairs && ok; ++pr, src += 2 * BM * BK) ok = load_pair(src);
-        if (odd && ok) ok = load_block(src);
+        uint64_t pending = all_kb;
+        const long long t0 = clock64();
+        int spins = 0;
+        bool stamped = false;
+        while (pending && ok) {
+          uint64_t ready = pending;
+          if (s > 0) {
+            if (p.sync_mode == 1) {
+              const unsigned int v = p.poll_acquire ? ld_acquire_gpu(p.sync + mb) : ld_relaxed_gpu(p.sync + mb);
+              ready = ((int)(v - (unsigned)s * (unsigned)p.tiles_n) >= 0) ? pending : 0ull;
+            } else if (p.sync_mode == 2) {
+              const unsigned int* fl = p.sync + kSyncFlags + (size_t)mb * p.tiles_n;
+              if (kBwd) {                                       // k-block kb_base + lane is written by CTA kb_base + lane
+                bool r0 = false;
+                if (lane < num_kb) r0 = (int)(ld_relaxed_gpu(fl + kb_base + lane) - (unsigned)s) >= 0;
+                ready = (uint64_t)__ballot_sync(0xffffffffu, r0);
+              } else {                                          // k-block j is written by CTAs 4j..4j+3; lane L reads flags 2L, 2L+1
+                bool r0 = false;
+                if (2 * lane < p.tiles_n) {
+                  const uint2 v2 = ld_relaxed_gpu_v2(fl + 2 * lane);
+                  r0 = ((int)(v2.x - (unsigned)s) >= 0) && ((int)(v2.y - (unsigned)s) >= 0);
+                }
+                const unsigned int b = __ballot_sync(0xffffffffu, r0);
+                unsigned int pr = b & (b >> 1) & 0x55555555u;   // bit 2j set <=> k-block j complete
+                pr = (pr | (pr >> 1)) & 0x33333333u; pr = (pr | (pr >> 2)) & 0x0f0f0f0fu;
+                pr = (pr | (pr >> 4)) & 0x00ff00ffu; pr = (pr | (pr >> 8)) & 0x0000ffffu;
+                ready = pr >> kb_base;
+              }
+            } else {
+              bool r0 = false, r1 = false;
+              if (lane < num_kb) r0 = (int)(ld_relaxed_gpu(ctr + lane * 32) - target) >= 0;
+              if (lane + 32 < num_kb) r1 = (int)(ld_relaxed_gpu(ctr + (lane + 32) * 32) - target) >= 0;
+              ready = (uint64_t)__ballot_sync(0xffffffffu, r0) | ((uint64_t)__ballot_sync(0xffffffffu, r1) << 32);
+            }
+            ready &= pending;
+            if (p.debug_mode == 3) {                            // experiment: in-order issue (lowest pending block first)
+              const uint64_t low = pending & (~pending + 1ull);
+              ready = (ready & low) ? low : 0ull;
+            }
+            if (!ready) {
+              if ((++spins & 63) == 0) {
+                if (*abort_flag) { ok = false; break; }
+                if (clock64() - t0 > kSpinLimit) { *abort_flag = 1; ok = false; break; }
+              }
+              continue;
+            }
+            // The producers' release made the tile image visible at L2 before the counter moved, and the only consumer is the
+            // async proxy (bulk copies read L2, issued after this control dependency): a generic-proxy acquire fence here
+            // costs an L2 round trip per batch of blocks and buys nothing.  The warp barrier orders polling lanes before the
+            // elected lane, the proxy fence orders generic observations before the async-proxy reads.
+            __syncwarp();
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+          }
+          if (p.dbg && blockIdx.x == 0 && lane == 0 && tile == 0 && !stamped) { p.dbg[4 * s + 0] = gtime(); stamped = true; }
+          pending &= ~ready;
+          while (ready && ok) {
+            const int ka = __ffsll((long long)ready) - 1;
+            ready &= ready - 1ull;
+            if (ready) {
+              const int kb2 = __ffsll((long long)ready) - 1;
+              ready &= ready - 1ull;
+              ok = load_pair(src, ka, kb2);
+            } else {
+              ok = load_block(src, ka);
+            }
+          }
+        }
       }
     }
   } else if (warp == 1) {
     // ======================================================================== MMA issuer
-    constexpr uint32_t idesc = tc::make_idesc_bf16_f32(BM, BN);
+    constexpr uint32_t idesc = tc::make_idesc_bf16_f32(BM, kBNm);
     bool ok = kStream ? true : wait_bar<false>(&ss->w_full, 0, abort_flag);
     const uint32_t full0 = tc::smem_u32(&ss->full[0]), empty0 = tc::smem_u32(&ss->empty[0]);
     const uint32_t tfull0 = tc::smem_u32(&ss->tmem_full[0]);
@@ -300,13 +435,17 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
     const uint64_t desc_w0 = tc::desc_kmajor_sw128(tc::smem_u32(smem_w));      // + kb * (kWBlockBytes >> 4)
     uint32_t stage = 0, phase = 0;
     const bool prof = p.dbg && blockIdx.x == 0;
-    constexpr int kGroup = kStages >= 5 ? 4 : 2;              // k-blocks per turn: all their try_waits are in flight together
-    for (int s = kBwd ? 1 : 0; s < steps && ok; ++s) {
+    constexpr int kGroup = (kStages >= 5 && !kFSplit) ? 4 : 2;   // k-blocks per turn: all their try_waits are in flight together
+    int steps_done = 0;
+    for (int s = kBwd ? 1 : 0; s < steps && ok; ++s, ++steps_done) {
      long long t_wait = 0, t_begin = prof ? clock64() : 0, t_first = 0;
      for (int tile = 0; tile < kTiles && ok; ++tile) {
-      uint64_t db = desc_w0;
-      const uint32_t acc = tmem_d + tile * BN;
+      const uint32_t acc = tmem_d + tile * kBNm;
       const uint32_t tfull = tfull0 + 8 * tile;
+      // operand k-blocks of the next step can arrive (from faster CTAs) while this CTA's epilogue still reads the
+      // accumulator of the previous one: the first MMA of a step overwrites it, so wait for the epilogue's hand-back
+      if (steps_done > 0) ok = wait_bar<false>(&ss->tmem_empty[tile], (uint32_t)((steps_done - 1) & 1), abort_flag);
+      if (!ok) break;
       for (int kb = 0; kb < num_kb && ok; kb += kGroup) {
         const int g = (num_kb - kb) < kGroup ? (num_kb - kb) : kGroup;
         uint32_t st[kGroup], ph[kGroup];
@@ -330,6 +469,10 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
         // all stages of the group have landed: issue its 4*g MMAs back to back (measured faster than issuing each
         // k-block as soon as its own stage lands: one fence + one elect per turn instead of per k-block)
         tc::fence_after_sync();
+        uint32_t kbi[kGroup];                                   // stages carry k-blocks in arrival order
+#pragma unroll
+        for (int i = 0; i < kGroup; ++i)       // (grid-barrier mode streams in order: no shared-memory round trip)
+          kbi[i] = (kStream || i >= g) ? 0u : (p.sync_mode == 1 ? (uint32_t)(kb + i) : ss->kb_idx[st[i]]);
         if (tc::elect_one()) {
 #pragma unroll
           for (int i = 0; i < kGroup; ++i) {
@@ -338,7 +481,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
                 tc::mbar_arrive(&ss->empty[st[i]]);
               } else {
                 const uint64_t da = desc_a0 + (uint64_t)(st[i] * (kStageBytes >> 4));
-                const uint64_t dbi = kStream ? da + (uint64_t)(kABytes >> 4) : db + (uint64_t)(i * (kWBlockBytes >> 4));
+                const uint64_t dbi = kStream ? da + (uint64_t)(kABytes >> 4) : desc_w0 + (uint64_t)(kbi[i] * (kWBlk >> 4));
                 if (kb == 0 && i == 0) tc::mma_bf16_ss_first(acc, da, dbi, idesc); else tc::mma_bf16_ss_acc(acc, da, dbi, idesc);
                 tc::mma_bf16_ss_acc(acc, da + 2, dbi + 2, idesc);
                 tc::mma_bf16_ss_acc(acc, da + 4, dbi + 4, idesc);
@@ -351,7 +494,6 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
         }
         __syncwarp();
         if (!ok) break;
-        db += (uint64_t)(g * (kWBlockBytes >> 4));
 #pragma unroll
         for (int i = 0; i < kGroup; ++i)
           if (i < g) { if (++stage == kStages) { stage = 0; phase ^= 1; } }
@@ -373,14 +515,29 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
     bool ok = true;
     const bool dbg_thread = p.dbg && blockIdx.x == 0 && etid == 0;
     auto epi_bar = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    // MEMBAR.ALL.GPU (the release of the dataflow signal) drains EVERY outstanding store of the SM, not just the signalling
+    // thread's: if the other 255 threads start their 57 KB of bookkeeping stores (h_seq / c_seq / activations) meanwhile, the
+    // signal - the only thing the other CTAs wait for - is held back by 1-3 us (measured).  They wait for it instead.
+    auto signal_sent_bar = [&]() { asm volatile("bar.sync 2, 256;" ::: "memory"); };
     // grid-barrier arrive: the CTA barrier orders every epilogue thread's writes before this thread's release
     // (same pattern as cooperative-groups grid sync).  ONE gpu-scope release: each fence is a full L2 round trip
     // (~0.8 us) and three of them used to dominate the epilogue; the generic->async proxy fence is on the consumer side.
 
     if (!kBwd) {
-      const int j0 = nb * 16 + 8 * half;            // this thread's 8 hidden units
-      const int n0 = nb * 64 + 32 * half;           // = its 32 gate columns
+      const int j0 = in_mb * 16 + 8 * half;         // this thread's 8 hidden units
+      const int n0 = in_mb * 64 + 32 * half;        // = its 32 gate columns
       const float* bs = ss->bias + 32 * half;
+      uint32_t xphase = 0;
+      const uint32_t xbase = tc::smem_u32(smem_x);
+      const uint32_t xbar = tc::smem_u32(&ss->xchg_full[0]), fbar = tc::smem_u32(&ss->xchg_free[0]);
+      const uint32_t pbar = kFSplit ? mapa(xbar, (uint32_t)(1 - ks)) : 0u;      // the peer's exchange barrier
+      float cst[kTiles][8];
+#pragma unroll
+      for (int tile = 0; tile < kTiles; ++tile) {
+        const int row = (mb0 + tile) * BM + rloc;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cst[tile][i] = row < B ? p.c_seq[(size_t)row * H + j0 + i] : 0.f;     // c_0 (written by the prologue)
+      }
       for (int t = 0; t < p.T && ok; ++t) {
 #pragma unroll
         for (int tile = 0; tile < kTiles; ++tile) {
@@ -388,15 +545,11 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
           const int row = mb * BM + rloc;
           const bool valid = row < B;
           // operands that do not depend on the GEMM: issue their loads before waiting on the accumulator
-          uint4 gxv[4];
-          float4 cv[2];
+          U8 gxw[2];
           if (valid) {
             const __nv_bfloat16* gp = p.gx + ((size_t)t * B + row) * (4 * H) + n0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) gxv[i] = ldg_nc16(gp + 8 * i);
-            const float* cp = p.c_seq + ((size_t)t * B + row) * H + j0;
-            cv[0] = *reinterpret_cast<const float4*>(cp); cv[1] = *reinterpret_cast<const float4*>(cp + 4);
-            if (t + 2 < p.T) prefetch_l2(gp + (size_t)2 * B * (4 * H));     // the x-projection comes from HBM: pull it into L2 early
+            gxw[0] = ldg_nc32(gp); gxw[1] = ldg_nc32(gp + 16);
+            if (t + 2 < p.T && p.debug_mode != 6) prefetch_l2(gp + (size_t)2 * B * (4 * H));     // the x-projection comes from HBM: pull it into L2 early
           }
           ok = wait_bar<false>(&ss->tmem_full[tile], tphase, abort_flag);
           if (!ok) break;
@@ -405,22 +558,61 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
           if (p.dbg && t == 8 && etid == 0) t_acc = gtime();
           if (dbg_thread && tile == 0) p.dbg[4 * t + 1] = gtime();
           uint32_t v[32];
-          tc::tmem_ld32(taddr0 + tile * BN, v);
-          tc::tmem_ld_wait();
-          tc::fence_before_sync();
+          if constexpr (kFSplit) {
+            // partial sums over this member's K half: columns [64 ks, +64) are mine, the other 64 go to the peer (bf16, DSMEM)
+            const uint32_t tb = tmem_d + ((uint32_t)(quarter * 32) << 16) + 32 * half;
+            uint32_t u[32];
+            tc::tmem_ld32(tb + 64 * (1 - ks), u);
+            tc::tmem_ld32(tb + 64 * ks, v);
+            tc::tmem_ld_wait();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&ss->tmem_empty[tile]);     // the issuer may overwrite the accumulator
+            if (t > 0) {                                               // the peer has consumed last step's partial
+              ok = wait_bar<true>(&ss->xchg_free[0], (uint32_t)((t - 1) & 1), abort_flag);
+              if (!ok) break;
+            }
+            const uint32_t drow = mapa(xbase + (uint32_t)(rloc * 128), (uint32_t)(1 - ks));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) pk[k] = pack_bf2(__uint_as_float(u[8 * i + 2 * k]), __uint_as_float(u[8 * i + 2 * k + 1]));
+              st_async_u4(drow + (uint32_t)((((4 * half + i) ^ (rloc & 7))) * 16), make_uint4(pk[0], pk[1], pk[2], pk[3]), pbar);
+            }
+            ok = wait_bar<true>(&ss->xchg_full[0], xphase, abort_flag);
+            if (!ok) break;
+            xphase ^= 1;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 x4 = *reinterpret_cast<const uint4*>(smem_x + (size_t)rloc * 128 + (((4 * half + i) ^ (rloc & 7)) * 16));
+              const uint32_t w[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                v[8 * i + 2 * k] = __float_as_uint(__uint_as_float(v[8 * i + 2 * k]) + bf_lo(w[k]));
+                v[8 * i + 2 * k + 1] = __float_as_uint(__uint_as_float(v[8 * i + 2 * k + 1]) + bf_hi(w[k]));
+              }
+            }
+          } else {
+            tc::tmem_ld32(taddr0 + tile * BN, v);
+            tc::tmem_ld_wait();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&ss->tmem_empty[tile]);     // the issuer may overwrite the accumulator
+          }
           if (dbg_thread && t == 8 && tile == 0) p.dbg[4 * (p.T + 2) + 0] = gtime();
           float cn[8], hv[8];
           uint32_t apk[16];
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
-            const uint4 g4 = gxv[jj >> 1];
-            const uint32_t ga = (jj & 1) ? g4.z : g4.x, gb = (jj & 1) ? g4.w : g4.y;
+            const uint32_t ga = gxw[jj >> 2].v[2 * (jj & 3)], gb = gxw[jj >> 2].v[2 * (jj & 3) + 1];
             const float pi = __uint_as_float(v[4 * jj + 0]) + bf_lo(ga) + bs[4 * jj + 0];
             const float pf = __uint_as_float(v[4 * jj + 1]) + bf_hi(ga) + bs[4 * jj + 1];
             const float pg = __uint_as_float(v[4 * jj + 2]) + bf_lo(gb) + bs[4 * jj + 2];
             const float po = __uint_as_float(v[4 * jj + 3]) + bf_hi(gb) + bs[4 * jj + 3];
             const float ig = ts::sigmoidf_fast(pi), fg = ts::sigmoidf_fast(pf), gg = ts::tanhf_fast(pg), og = ts::sigmoidf_fast(po);
-            const float c = fg * reinterpret_cast<const float*>(cv)[jj] + ig * gg;
+            const float c = fg * cst[tile][jj] + ig * gg;
+            cst[tile][jj] = c;                        // the cell state never leaves the registers of its thread
             cn[jj] = c;
             hv[jj] = og * ts::tanhf_fast(c);
             apk[2 * jj] = pack_bf2(ig, fg);
@@ -442,17 +634,27 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
               p.dbg[4 * (p.T + 2) + 64 + 2 * blockIdx.x] = t_acc;
               p.dbg[4 * (p.T + 2) + 64 + 2 * blockIdx.x + 1] = gtime();
             }
-            signal_counter(p.sync + mb);
+            // this CTA's 16 hidden units = a quarter of k-block nb/4
+            if (p.sync_mode == 1) signal_counter(p.sync + mb);
+            else if (p.sync_mode == 2) st_release_gpu(p.sync + kSyncFlags + (size_t)mb * p.tiles_n + in_mb, (unsigned)(t + 1));
+            else signal_counter(p.sync + kSyncKb + ((size_t)mb * (H / BK) + (in_mb >> 2)) * 32);
             if (dbg_thread && tile == 0) p.dbg[4 * t + 2] = gtime();
           }
-          if (valid) {                                   // everything below is off the critical path
+          // (after the CTA barrier every epilogue thread is done with this step's exchange buffer)
+          if (kFSplit && etid == 32) {
+            tc::mbar_expect_tx_u32(xbar, (uint32_t)kXchgBytes);        // arm the next phase, THEN let the peer overwrite the buffer
+            mbar_arrive_remote_relaxed(mapa(fbar, (uint32_t)(1 - ks)));
+          }
+          signal_sent_bar();
+          if (valid && p.debug_mode != 5) {              // everything below is off the critical path
             stg16(p.h_seq + ((size_t)(t + 1) * B + row) * H + j0, h8);
             float* cp = p.c_seq + ((size_t)(t + 1) * B + row) * H + j0;
-            *reinterpret_cast<float4*>(cp) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-            *reinterpret_cast<float4*>(cp + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+            stg32(cp, __float_as_uint(cn[0]), __float_as_uint(cn[1]), __float_as_uint(cn[2]), __float_as_uint(cn[3]),
+                  __float_as_uint(cn[4]), __float_as_uint(cn[5]), __float_as_uint(cn[6]), __float_as_uint(cn[7]));
             __nv_bfloat16* ap = p.act + ((size_t)t * B + row) * (4 * H) + n0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) stg16(ap + 8 * i, make_uint4(apk[4 * i], apk[4 * i + 1], apk[4 * i + 2], apk[4 * i + 3]));
+            for (int i = 0; i < 2; ++i)
+              stg32(ap + 16 * i, apk[8 * i], apk[8 * i + 1], apk[8 * i + 2], apk[8 * i + 3], apk[8 * i + 4], apk[8 * i + 5], apk[8 * i + 6], apk[8 * i + 7]);
           }
         }
         tphase ^= 1;
@@ -488,17 +690,15 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
           uint8_t* xbuf = smem_x + tile * kXchgBytes;               // [4 src][128 rows][16 bf16]
           const uint32_t xbase = tc::smem_u32(xbuf);
           const uint32_t xbar = tc::smem_u32(&ss->xchg_full[tile]);
-          uint4 av[4], dhv;
-          float4 cpv[2], cnv[2];
+          U8 avw[2], cpv, cnv;
+          uint4 dhv;
           if (valid && s < p.T) {
             const __nv_bfloat16* ap = p.act + ((size_t)t * B + row) * (4 * H) + 4 * j0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) av[i] = ldg_nc16(ap + 8 * i);
+            avw[0] = ldg_nc32(ap); avw[1] = ldg_nc32(ap + 16);
             dhv = ldg_nc16(p.dh_seq + ((size_t)t * B + row) * H + j0);
             const float* c0p = p.c_seq + ((size_t)t * B + row) * H + j0;
             const float* c1p = p.c_seq + ((size_t)(t + 1) * B + row) * H + j0;
-            cpv[0] = *reinterpret_cast<const float4*>(c0p); cpv[1] = *reinterpret_cast<const float4*>(c0p + 4);
-            cnv[0] = *reinterpret_cast<const float4*>(c1p); cnv[1] = *reinterpret_cast<const float4*>(c1p + 4);
+            cpv = ldg_nc32(c0p); cnv = ldg_nc32(c1p);
             if (t >= 2) {                                                      // saved activations come from HBM: pull t-2 into L2 early
               prefetch_l2(ap - (size_t)2 * B * (4 * H));
               prefetch_l2(c0p - (size_t)2 * B * H);
@@ -514,6 +714,14 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
             tc::tmem_ld32(taddr0 + tile * BN, v);
             tc::tmem_ld_wait();
             tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&ss->tmem_empty[tile]);     // the issuer may overwrite the accumulator
+            // A member only needs the dG blocks of ITS K-quarter, so nothing in the dataflow stops a fast member from being a
+            // whole step ahead of a slow one: explicit back-pressure before overwriting anybody's exchange buffer.
+            if (s > 1) {
+              ok = wait_bar<true>(&ss->xchg_free[tile], (uint32_t)(s & 1), abort_flag);
+              if (!ok) break;
+            }
             // reduce-scatter over the 4 K-quarters: column chunk q (16 wide, bf16) goes to member q's slot [ks] (DSMEM)
 #pragma unroll
             for (int qq = 0; qq < 2; ++qq) {
@@ -521,11 +729,10 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
               uint32_t pk[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) pk[i] = pack_bf2(__uint_as_float(v[16 * qq + 2 * i]), __uint_as_float(v[16 * qq + 2 * i + 1]));
-              st_cluster_u4(dst, make_uint4(pk[0], pk[1], pk[2], pk[3]));
-              st_cluster_u4(dst + 16, make_uint4(pk[4], pk[5], pk[6], pk[7]));
+              const uint32_t dbar = mapa(xbar, (uint32_t)(2 * half + qq));
+              st_async_u4(dst, make_uint4(pk[0], pk[1], pk[2], pk[3]), dbar);
+              st_async_u4(dst + 16, make_uint4(pk[4], pk[5], pk[6], pk[7]), dbar);
             }
-            epi_bar();
-            if (etid < 4) mbar_arrive_remote(mapa(xbar, (uint32_t)etid));
             ok = wait_bar<true>(&ss->xchg_full[tile], xphase, abort_flag);
             if (!ok) break;
 #pragma unroll
@@ -551,13 +758,12 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
           uint32_t gpk[16];
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
-            const uint4 a4 = av[jj >> 1];
-            const uint32_t aa = (jj & 1) ? a4.z : a4.x, ab = (jj & 1) ? a4.w : a4.y;
+            const uint32_t aa = avw[jj >> 2].v[2 * (jj & 3)], ab = avw[jj >> 2].v[2 * (jj & 3) + 1];
             const float ig = bf_lo(aa), fg = bf_hi(aa), gg = bf_lo(ab), og = bf_hi(ab);
             const uint32_t dw = (jj >> 1) == 0 ? dhv.x : (jj >> 1) == 1 ? dhv.y : (jj >> 1) == 2 ? dhv.z : dhv.w;
             const float dht = dh[tile][jj] + ((jj & 1) ? bf_hi(dw) : bf_lo(dw));
-            const float cprev = reinterpret_cast<const float*>(cpv)[jj];
-            const float tcn = ts::tanhf_fast(reinterpret_cast<const float*>(cnv)[jj]);
+            const float cprev = __uint_as_float(cpv.v[jj]);
+            const float tcn = ts::tanhf_fast(__uint_as_float(cnv.v[jj]));
             const float dct = dc[tile][jj] + dht * og * (1.f - tcn * tcn);
             const float d_o = dht * tcn, d_i = dct * gg, d_f = dct * cprev, d_g = dct * ig;
             dc[tile][jj] = dct * fg;
@@ -574,13 +780,24 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
           }
           epi_bar();
           if (etid == 0) {
-            signal_counter(p.sync + mb);
+            // this CTA's 64 gate columns = dG k-block 4 nb + ks
+            if (p.sync_mode == 1) signal_counter(p.sync + mb);
+            else if (p.sync_mode == 2) st_release_gpu(p.sync + kSyncFlags + (size_t)mb * p.tiles_n + in_mb, (unsigned)(s + 1));
+            else signal_counter(p.sync + kSyncKb + ((size_t)mb * (4 * H / BK) + in_mb) * 32);
             if (dbg_thread && tile == 0) p.dbg[4 * s + 2] = gtime();
           }
+          // (the CTA barrier above also means every epilogue thread is done reading this step's exchange buffer)
+          if (s > 0) {
+            if (etid == 32) tc::mbar_expect_tx_u32(xbar, (uint32_t)kXchgBytes);    // arm the next phase, THEN free the buffer
+            __syncwarp();
+            if (etid >= 32 && etid < 36) mbar_arrive_remote_relaxed(mapa(tc::smem_u32(&ss->xchg_free[tile]), (uint32_t)(etid - 32)));
+          }
+          signal_sent_bar();
           if (valid) {                                   // the [T,B,4H] copy for the weight-gradient GEMMs: off the critical path
             __nv_bfloat16* gp = p.dpre + ((size_t)t * B + row) * (4 * H) + 4 * j0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) stg16(gp + 8 * i, make_uint4(gpk[4 * i], gpk[4 * i + 1], gpk[4 * i + 2], gpk[4 * i + 3]));
+            for (int i = 0; i < 2; ++i)
+              stg32(gp + 16 * i, gpk[8 * i], gpk[8 * i + 1], gpk[8 * i + 2], gpk[8 * i + 3], gpk[8 * i + 4], gpk[8 * i + 5], gpk[8 * i + 6], gpk[8 * i + 7]);
           }
         }
         if (s > 0) { tphase ^= 1; xphase ^= 1; }
@@ -590,8 +807,8 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
 
   tc::fence_before_sync();
   __syncthreads();
-  if (kBwd) cluster_sync_all();                  // nobody exits while a peer may still write into / arrive on its smem
-  if (threadIdx.x == 0 && ss->abort_flag) atomicExch(reinterpret_cast<int*>(p.sync + 63), 1);
+  if (kCluster) cluster_sync_all();              // nobody exits while a peer may still write into / arrive on its smem
+  if (threadIdx.x == 0 && ss->abort_flag) atomicExch(reinterpret_cast<int*>(p.sync + kSyncErr), 1);
   if (warp == 2) tc::tmem_dealloc(tmem_d, kTmemCols);
 }
 
@@ -615,18 +832,21 @@ __global__ void seq_prologue_kernel(const __nv_bfloat16* __restrict__ h0, const 
   const int n4 = B * H / 4;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x)
     reinterpret_cast<float4*>(c_seq0)[i] = reinterpret_cast<const float4*>(c0)[i];
-  if (blockIdx.x == 0 && threadIdx.x < 16) sync[threadIdx.x] = 0u;
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < kSyncErr; i += blockDim.x) sync[i] = 0u;
 }
 
-size_t smem_bytes(int H, bool bwd, int stages, int tiles, bool stream = false) {
+size_t smem_bytes(int H, bool bwd, int stages, int tiles, bool stream = false, bool fsplit = false) {
   const size_t ring = (size_t)stages * (stream ? kABytes + kWBlockBytes : kABytes);
-  return (stream ? 0 : (size_t)(H / BK) * kWBlockBytes) + ring + (bwd ? tiles * kXchgBytes : 0) + sizeof(SeqSmem) + 1024;
+  // resident weights: H/64 blocks of [64 x 64] (forward K-split: H/128 blocks of [128 x 64] = the same bytes)
+  return (stream ? 0 : (size_t)(H / BK) * kWBlockBytes) + ring + ((bwd || fsplit) ? tiles * kXchgBytes : 0) + sizeof(SeqSmem) + 1024;
 }
 
-template <bool kBwd, int kStages, int kTiles, bool kStream = false>
+template <bool kBwd, int kStages, int kTiles, bool kStream = false, bool kFSplit = false>
 int launch_cfg(const CUtensorMap& tw, const SeqParams& p, int grid, cudaStream_t st) {
-  auto kern = lstm_seq_kernel<kBwd, kStages, kTiles, kStream>;
-  const size_t smem = smem_bytes(p.H, kBwd, kStages, kTiles, kStream);
+  auto kern = lstm_seq_kernel<kBwd, kStages, kTiles, kStream, kFSplit>;
+  const size_t smem = smem_bytes(p.H, kBwd, kStages, kTiles, kStream, kFSplit);
+  constexpr int kClusterDim = kBwd ? 4 : (kFSplit ? 2 : 1);
   if (smem > 227 * 1024) return -4;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
@@ -634,20 +854,31 @@ int launch_cfg(const CUtensorMap& tw, const SeqParams& p, int grid, cudaStream_t
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = kBwd ? 4 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[0].val.clusterDim.x = kClusterDim; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  if (kBwd) {
+  if (kClusterDim > 1) {
     int nclusters = 0;
     e = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
     if (e != cudaSuccess) { cudaGetLastError(); return -20; }
-    if (nclusters * 4 < grid) return -21;              // not co-resident
+    if (nclusters * kClusterDim < grid) return -21;    // not co-resident
   }
   e = cudaLaunchKernelEx(&cfg, kern, tw, p);
   return (int)e;
 }
 
 template <bool kBwd>
-int dispatch(const CUtensorMap& tw, const SeqParams& p, int grid, int stages, int tiles, bool stream, cudaStream_t st) {
+int dispatch(const CUtensorMap& tw, const SeqParams& p, int grid, int stages, int tiles, bool stream, bool fsplit, cudaStream_t st) {
+  if constexpr (!kBwd) {
+    if (fsplit) {                                  // forward K-split (cluster of 2), one batch tile per CTA
+      switch (stages) {
+        case 3: return launch_cfg<false, 3, 1, false, true>(tw, p, grid, st);
+        case 4: return launch_cfg<false, 4, 1, false, true>(tw, p, grid, st);
+        case 5: return launch_cfg<false, 5, 1, false, true>(tw, p, grid, st);
+        case 6: return launch_cfg<false, 6, 1, false, true>(tw, p, grid, st);
+      }
+      return -5;
+    }
+  }
   if (stream) {                                    // streamed weights: 24 KB stages, one batch tile per CTA
     switch (stages) {
       case 4: return launch_cfg<kBwd, 4, 1, true>(tw, p, grid, st);
@@ -684,7 +915,7 @@ int pick_stages(int H, bool bwd, int tiles) {
 
 }  // namespace
 
-// sync_ws: >= 64 u32; [0..tiles_m) step counters (zeroed by the caller before every launch), [63] sticky error flag.
+// sync_ws: kSyncWords u32 (layout above); everything but the sticky error flag in the last word is zeroed before every launch.
 // variant (tuning knob, 0 = defaults) = tiles_per_cta + 16*stages + 4096*debug_mode:  tiles_per_cta 0 -> 1 (set 2 to let a
 // CTA alternate two batch tiles);  stages 0 -> deepest ring that fits next to the resident weight slice.
 template <bool kBwd>
@@ -693,28 +924,38 @@ static int seq_common(SeqParams& p, const void* w_base, int variant, cudaStream_
   if (H % 64 != 0) { ts::set_last_error("lstm_seq: H must be a multiple of 64"); return -2; }
   const int tiles_m = (B + BM - 1) / BM, tiles_n = kBwd ? (H / BN) * 4 : 4 * H / BN;
   int stages = (variant >> 4) & 15, tiles = variant & 15;
-  p.debug_mode = (variant >> 12) & 3;
+  p.debug_mode = (variant >> 12) & 7;
+  p.sync_mode = (variant >> 16) & 3;
+  p.poll_acquire = (variant >> 18) & 1;
   if (tiles != 2 || tiles_m % 2 != 0) tiles = 1;
   // resident weight slice if it fits next to >= 4 ring stages, else stream the weights through the ring
   const bool stream = smem_bytes(H, kBwd, 4, 1) > 227 * 1024 || ((variant >> 8) & 1);
   if (stream) tiles = 1;
+  // forward: 2-way K split (cluster of 2) unless disabled by variant bit 19
+  const bool fsplit = !kBwd && !stream && tiles == 1 && H % 128 == 0 && !((variant >> 19) & 1) &&
+                      smem_bytes(H, false, 3, 1, false, true) <= 227 * 1024;
   int dev = 0;
   cudaGetDevice(&dev);
   const int grid = (tiles_m / tiles) * tiles_n;
   if (grid > ts::sm_count(dev)) { ts::set_last_error("lstm_seq: grid exceeds SM count (not co-resident)"); return -3; }
   if (stream) {
     if (stages != 4 && stages != 6 && stages != 8) stages = smem_bytes(H, kBwd, 8, 1, true) <= 227 * 1024 ? 8 : 6;
+  } else if (fsplit) {
+    if (stages < 3 || stages > 6 || smem_bytes(H, false, stages, 1, false, true) > 227 * 1024) {
+      stages = 6;
+      while (stages > 3 && smem_bytes(H, false, stages, 1, false, true) > 227 * 1024) --stages;
+    }
   } else {
     if (stages == 0) stages = pick_stages(H, kBwd, tiles);
     if (stages < 2 || smem_bytes(H, kBwd, stages, tiles) > 227 * 1024) { ts::set_last_error("lstm_seq: weight slice does not fit in shared memory"); return -4; }
   }
   const int K = kBwd ? 4 * H : H, N = kBwd ? H : 4 * H;
   CUtensorMap tw;
-  if (int rc = ts::make_tmap_2d_bf16(&tw, w_base, (uint64_t)N, (uint64_t)K, (uint64_t)K, BK, BN)) return rc;
+  if (int rc = ts::make_tmap_2d_bf16(&tw, w_base, (uint64_t)N, (uint64_t)K, (uint64_t)K, BK, fsplit ? 2 * BN : BN)) return rc;
   p.tiles_n = tiles_n;
   p.tiles_m = tiles_m;
-  int rc = dispatch<kBwd>(tw, p, grid, stages, tiles, stream, st);
-  if (rc == -21) ts::set_last_error("lstm_seq_bwd: clusters of 4 are not co-resident on this device");
+  int rc = dispatch<kBwd>(tw, p, grid, stages, tiles, stream, fsplit, st);
+  if (rc == -21) ts::set_last_error("lstm_seq: the thread-block clusters are not co-resident on this device");
   return rc;
 }
 
@@ -739,7 +980,7 @@ extern "C" int ts_lstm_seq_fwd(const void* gx, const void* w_h, const float* bia
 extern "C" int ts_lstm_seq_bwd(const void* dh_seq, const void* w_hT, const void* act, const float* c_seq, const void* dpre,
                                float* dh0, float* dc0, void* dbg, void* a_tiled, int T, int B, int H, unsigned int* sync_ws, int variant,
                                cudaStream_t st) {
-  cudaMemsetAsync(sync_ws, 0, 16 * sizeof(unsigned int), st);      // step counters restart at 0 every launch
+  cudaMemsetAsync(sync_ws, 0, kSyncErr * sizeof(unsigned int), st);      // arrival counters restart at 0 every launch
   SeqParams p{};
   p.a_tiled = (__nv_bfloat16*)a_tiled;
   p.dh_seq = (const __nv_bfloat16*)dh_seq; p.act = (__nv_bfloat16*)act; p.c_seq = (float*)c_seq; p.dpre = (__nv_bfloat16*)dpre;

@@ -65,17 +65,20 @@ def _accumulate_grad(w_addr: int, a_t: torch.Tensor, b: torch.Tensor):
     return _mm_f32(a_t, b)
 
 
+SYNC_WORDS = 8192        # csrc/lstm_seq_tcgen05.cu kSyncWords; the last word is the sticky error flag
+
+
 def _sync_ws(device) -> torch.Tensor:
     key = (device.type, device.index)
     if key not in _SYNC_WS:
-        _SYNC_WS[key] = torch.zeros(64, dtype=torch.int32, device=device)
+        _SYNC_WS[key] = torch.zeros(SYNC_WORDS, dtype=torch.int32, device=device)
     return _SYNC_WS[key]
 
 
 def check_kernel_errors(device) -> None:
     """Raise if a persistent kernel hit its bounded-spin timeout (sticky flag, costs one D2H read)."""
     ws = _SYNC_WS.get((device.type, device.index))
-    if ws is not None and int(ws[63].item()) != 0:
+    if ws is not None and int(ws[SYNC_WORDS - 1].item()) != 0:
         raise RuntimeError("lstm_seq kernel aborted: an in-kernel wait timed out (see csrc/lstm_seq_tcgen05.cu)")
 
 
