@@ -199,13 +199,14 @@ std::vector<Tensor> lstm_seq_fwd(const Tensor& gx, const Tensor& w_h, const Tens
   return {h_seq, c_seq, act};
 }
 
-// dh_seq [T,B,H] bf16 (grad wrt every h_t from above), w_hT [H,4H] bf16 (transposed recurrent weights),
+// dh_seq [T,B,H] bf16 (grad wrt every h_t from above; None when only h_T is used downstream), w_hT [H,4H] bf16 (transposed recurrent weights),
 // act/c_seq from forward, dhT fp32 [B,H] / dcT fp32 [B,H] extra grads into the final state (may be zeros)
 // -> dpre [T,B,4H] bf16, dh0 fp32 [B,H], dc0 fp32 [B,H]
-std::vector<Tensor> lstm_seq_bwd(const Tensor& dh_seq, const Tensor& w_hT, const Tensor& act, const Tensor& c_seq,
+std::vector<Tensor> lstm_seq_bwd(const std::optional<Tensor>& dh_seq, const Tensor& w_hT, const Tensor& act, const Tensor& c_seq,
                                  const Tensor& dhT, const Tensor& dcT, Tensor sync_ws, int64_t variant,
                                  std::optional<Tensor> dbg) {
-  chk_cuda(dh_seq, "dh_seq"); chk_cuda(w_hT, "w_hT"); chk_cuda(act, "act"); chk_cuda(c_seq, "c_seq");
+  if (dh_seq.has_value()) chk_cuda(*dh_seq, "dh_seq");
+  chk_cuda(w_hT, "w_hT"); chk_cuda(act, "act"); chk_cuda(c_seq, "c_seq");
   c10::cuda::CUDAGuard gd(act.device());
   int T = act.size(0), B = act.size(1), H = act.size(2) / 4;
   auto dpre = torch::empty_like(act);
@@ -213,7 +214,7 @@ std::vector<Tensor> lstm_seq_bwd(const Tensor& dh_seq, const Tensor& w_hT, const
   auto dc0 = dcT.clone();
   const int tiles_m = (B + 127) / 128;
   auto tiled = torch::empty({(int64_t)T, tiles_m, 4 * H / 64, 128, 64}, act.options());   // dG images, written by the kernel
-  check(ts_lstm_seq_bwd(dh_seq.data_ptr(), w_hT.data_ptr(), act.data_ptr(), c_seq.data_ptr<float>(), dpre.data_ptr(),
+  check(ts_lstm_seq_bwd(dh_seq.has_value() ? dh_seq->data_ptr() : nullptr, w_hT.data_ptr(), act.data_ptr(), c_seq.data_ptr<float>(), dpre.data_ptr(),
                         dh0.data_ptr<float>(), dc0.data_ptr<float>(), dbg.has_value() ? dbg->data_ptr() : nullptr, tiled.data_ptr(), T, B, H,
                         (unsigned int*)sync_ws.data_ptr<int>(), (int)variant, stream()), "lstm_seq_bwd");
   return {dpre, dh0, dc0};

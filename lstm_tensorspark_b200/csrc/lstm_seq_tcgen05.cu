@@ -6,22 +6,29 @@
 // multi-step unroll its fit_next API was built for (lstm.py:128-136).
 //
 // Design (B200-first):
-//   * Every CTA keeps a [64 x H] bf16 slice of the recurrent weights RESIDENT in shared memory for all T steps
-//     (loaded once by TMA; W_h is 8 MB at H=1024 = 128 CTAs x 64 KB..128 KB).  Rows are gate-interleaved (n = 4j+g) so
-//     a CTA that owns a row slice owns complete (i,f,g,o) quadruples: the gate epilogue needs no cross-CTA traffic.
-//   * Per step a CTA streams a 128-row batch tile of h_{t-1} (forward) / dG_{t+1} (backward) through a TMA->mbarrier
-//     ring; one elected thread issues tcgen05.mma (M=128, N=64, K=16, bf16 -> fp32 accumulators in TMEM); four epilogue
-//     warps read the accumulator with tcgen05.ld and do the whole cell in registers.
-//   * The streamed operand is the L2-bandwidth bottleneck (every CTA of a batch tile needs all of it).  Forward:
-//     CTAs that share a batch tile form a thread-block CLUSTER and each k-block is fetched from L2 once and
-//     TMA-MULTICAST into all members.  Backward: the contraction runs over 4H, so a cluster of 4 CTAs splits K
-//     (one gate-column quarter each, 4x less operand traffic than a single-CTA K=4H loop) and the four partial
-//     [128 x 64] tiles are reduce-scattered through DISTRIBUTED SHARED MEMORY (st.shared::cluster + remote mbarrier
-//     arrive); each member then owns 16 hidden columns of dh for the gate-gradient epilogue.
-//   * Steps are separated by a grid-wide dataflow barrier in global memory (one monotonically increasing counter per
-//     batch tile, red.release.gpu / ld.acquire.gpu, generic->async proxy fences because the consumer is TMA).
-//     All CTAs are co-resident (grid <= #SMs, 1 CTA/SM, checked with cudaOccupancyMaxActiveClusters); every spin is
-//     bounded and raises an error flag instead of hanging the GPU.
+//   * Every CTA keeps a bf16 slice of the recurrent weights RESIDENT in shared memory for all T steps (loaded once by
+//     TMA; W_h is 8 MB at H=1024 = 128 CTAs x 128 KB).  Rows are gate-interleaved (n = 4j+g) so a CTA that owns a row
+//     slice owns complete (i,f,g,o) quadruples: the gate epilogue needs no cross-CTA traffic.
+//   * Per step a CTA streams a 128-row batch tile of h_{t-1} (forward) / dG_{t+1} (backward) through a bulk-copy ->
+//     mbarrier ring (the operand is kept in global memory as ready-made 128B-swizzled tile images, 16 KB contiguous per
+//     k-block); one elected thread issues tcgen05.mma (M=128, K=16, bf16 -> fp32 accumulators in TMEM); eight epilogue
+//     warps read the accumulator with tcgen05.ld and do the whole cell in registers (the cell state never leaves them).
+//   * The stream is bound by (bytes in flight) / (L2 latency), not by bandwidth: the ring next to a 128 KB weight slice
+//     holds 5-6 of the k-blocks.  So BOTH passes split K across a thread-block cluster - forward 2 CTAs (8 k-blocks each,
+//     N=128), backward 4 CTAs (one gate-column quarter each, N=64) - and reduce-scatter the partial accumulators through
+//     DISTRIBUTED SHARED MEMORY with st.async (bytes are counted on the receiver's mbarrier: no release/acquire fences,
+//     which the compiler lowers to MEMBAR.ALL.GPU even at cluster scope).  Every member then owns 16 hidden units.
+//   * Steps are not separated by a grid barrier but by DATAFLOW: every operand k-block has an arrival counter in global
+//     memory (its producer CTAs: epilogue stores -> CTA barrier -> ONE red.release.gpu); the producer warp's 32 lanes poll
+//     all counters of their K slice with relaxed loads and pull the blocks into the ring in arrival order (accumulation
+//     order is free; the ring stage carries its k-block id to the MMA issuer).  The consumer is the async proxy (L2),
+//     so there is no acquire fence; a tmem_empty mbarrier keeps the next step's first MMA off an accumulator that is
+//     still being read.
+//   * What a release costs decides the step time: MEMBAR.ALL.GPU drains every outstanding store of the SM, so the
+//     bookkeeping stores (h_seq / c_seq / activations for backward) are held back until the signal has left, and they are
+//     256-bit (STG.256): their L2 request COUNT, not their bytes, is what used to slow the operand stream down.
+//   * All CTAs are co-resident (grid <= #SMs, 1 CTA/SM, checked with cudaOccupancyMaxActiveClusters); every spin is
+//     bounded and raises a sticky error flag instead of hanging the GPU.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -202,7 +209,7 @@ struct SeqParams {
   float* c_seq;                // [T+1,B,H]   (row 0 = c0)
   __nv_bfloat16* act;          // [T,B,4H]
   // backward
-  const __nv_bfloat16* dh_seq; // [T,B,H]
+  const __nv_bfloat16* dh_seq; // [T,B,H] gradient into every h_t from above; null = only the final state has one (dh0 in)
   __nv_bfloat16* dpre;         // [T,B,4H]
   float* dh0;                  // [B,H] in: dL/dh_T extra, out: dL/dh_0
   float* dc0;                  // [B,H] in: dL/dc_T, out: dL/dc_0
@@ -223,9 +230,9 @@ struct SeqParams {
 //                                 cluster; after the DSMEM reduce-scatter member ks owns hidden [64 nb2 + 16 ks, +16).
 // Warps: 0 = producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, 4..11 = epilogue (warp % 4 = TMEM lane quarter,
 // (warp-4)/4 = which 32 of the 64 accumulator columns; one thread = one batch row x 8 hidden units).
-// The two role warps run CONVERGED and issue under elect.sync so descriptors / addresses stay in uniform registers;
-// k-blocks are handled in pairs (two overlapped mbarrier.try_wait, 8 MMAs per turn): the barrier turn-around, not the
-// tensor pipe (48 cycles per M128xN64xK16 instruction), is what bounds a step.
+// The two role warps run CONVERGED and issue under elect.sync so descriptors / addresses stay in uniform registers
+// (an `if (lane == 0)` role loop makes ptxas wrap every UTCHMMA / UBLKCP in a waterfall loop: ~590 cycles per k-block);
+// k-blocks are handled in groups (overlapped mbarrier.try_waits, one fence + one elect per group).
 // kTiles = 2: the CTA alternates TWO independent 128-row batch tiles (same resident weight slice): while one tile sits
 // in its epilogue + grid barrier (latency), the other one streams its operand and runs its MMAs.  Half as many CTAs are
 // needed (64 for B = 256, H = 1024), which leaves SMs free for the weight-gradient GEMMs that run concurrently.
@@ -435,7 +442,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
     const uint64_t desc_w0 = tc::desc_kmajor_sw128(tc::smem_u32(smem_w));      // + kb * (kWBlockBytes >> 4)
     uint32_t stage = 0, phase = 0;
     const bool prof = p.dbg && blockIdx.x == 0;
-    constexpr int kGroup = (kStages >= 5 && !kFSplit) ? 4 : 2;   // k-blocks per turn: all their try_waits are in flight together
+    constexpr int kGroup = (kStages >= 5 && !kFSplit && !kBwd) ? 4 : 2;   // k-blocks per turn: all their try_waits are in flight together
     int steps_done = 0;
     for (int s = kBwd ? 1 : 0; s < steps && ok; ++s, ++steps_done) {
      long long t_wait = 0, t_begin = prof ? clock64() : 0, t_first = 0;
@@ -695,14 +702,14 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
           if (valid && s < p.T) {
             const __nv_bfloat16* ap = p.act + ((size_t)t * B + row) * (4 * H) + 4 * j0;
             avw[0] = ldg_nc32(ap); avw[1] = ldg_nc32(ap + 16);
-            dhv = ldg_nc16(p.dh_seq + ((size_t)t * B + row) * H + j0);
+            dhv = p.dh_seq ? ldg_nc16(p.dh_seq + ((size_t)t * B + row) * H + j0) : make_uint4(0u, 0u, 0u, 0u);
             const float* c0p = p.c_seq + ((size_t)t * B + row) * H + j0;
             const float* c1p = p.c_seq + ((size_t)(t + 1) * B + row) * H + j0;
             cpv = ldg_nc32(c0p); cnv = ldg_nc32(c1p);
             if (t >= 2) {                                                      // saved activations come from HBM: pull t-2 into L2 early
               prefetch_l2(ap - (size_t)2 * B * (4 * H));
               prefetch_l2(c0p - (size_t)2 * B * H);
-              prefetch_l2(p.dh_seq + ((size_t)(t - 2) * B + row) * H + j0);
+              if (p.dh_seq) prefetch_l2(p.dh_seq + ((size_t)(t - 2) * B + row) * H + j0);
             }
           }
           if (s > 0) {
@@ -774,9 +781,16 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
             // next iteration's operand first: this thread's 32 gate columns = 4 chunks of row rloc of k-block j0/16
             const size_t blk = ((size_t)t * p.tiles_m + mb) * (4 * H / BK) + (j0 / 16);
             __nv_bfloat16* tp = p.a_tiled + blk * (BM * BK) + rloc * BK;
+            // chunk c of row r sits at c ^ (r & 7): an aligned chunk pair stays an aligned pair (32 B sector p ^ ((r & 7) >> 1)),
+            // swapped when r is odd -> two whole-sector 256-bit stores instead of four 16 B ones
+            const bool swp = rloc & 1;
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              stg16(tp + (((4 * half + i) ^ (rloc & 7)) * 8), make_uint4(gpk[4 * i], gpk[4 * i + 1], gpk[4 * i + 2], gpk[4 * i + 3]));
+            for (int k = 0; k < 2; ++k) {
+              const int sp = (2 * half + k) ^ ((rloc & 7) >> 1);
+              const uint32_t* a = gpk + 8 * k;
+              stg32(tp + sp * 16, swp ? a[4] : a[0], swp ? a[5] : a[1], swp ? a[6] : a[2], swp ? a[7] : a[3],
+                    swp ? a[0] : a[4], swp ? a[1] : a[5], swp ? a[2] : a[6], swp ? a[3] : a[7]);
+            }
           }
           epi_bar();
           if (etid == 0) {

@@ -54,7 +54,7 @@ class RNN(nn.Module):
         seq = input_data.transpose(0, 1)            # time-major [T,B,D]; the kernels index (t, b)
         for layer in self.layers:
             seq = layer.fit_sequence(seq)
-        return seq[-1]
+        return self.layers[-1].ht                   # = seq[-1], as a separate autograd edge (no [T,B,H] gradient for the top layer)
 
     def fit_sequence_all(self, input_data: torch.Tensor) -> torch.Tensor:
         """``[B,T,D]`` -> last layer's full ``h_seq [T,B,H]``."""

@@ -155,18 +155,23 @@ class _LSTMSeqFn(torch.autograd.Function):
         ctx.dims = (T, B, D, H)
         ctx.w_addrs = (w_x.data_ptr(), w_h.data_ptr())
         ctx.in_dtypes = (h0.dtype, c0.dtype)
-        return h_seq[1:], c_seq[T]
+        # h_T is its own output (not a slice of the first one taken by the caller): a consumer of the final state only - the
+        # classifier on top of the stack - then sends back a [B,H] gradient instead of a zero-filled [T,B,H] one
+        return h_seq[1:], h_seq[T], c_seq[T]
 
     @staticmethod
-    def backward(ctx, dh_seq, dc_T):
+    def backward(ctx, dh_seq, dh_T, dc_T):
         E = ext()
         x2d, h_seq, c_seq, act, w_x_c, w_h_c = ctx.saved_tensors
         T, B, D, H = ctx.dims
         cd = act.dtype
         dev = act.device
-        dh_seq = (dh_seq if dh_seq is not None else torch.zeros(T, B, H, dtype=cd, device=dev)).to(cd).contiguous()
+        if dh_seq is not None:
+            dh_seq = dh_seq.to(cd).contiguous()
+        elif not ctx.fast:
+            dh_seq = torch.zeros(T, B, H, dtype=cd, device=dev)
         dcT = (dc_T.float().contiguous() if dc_T is not None else torch.zeros(B, H, dtype=torch.float32, device=dev))
-        dhT = torch.zeros(B, H, dtype=torch.float32, device=dev)
+        dhT = (dh_T.float().contiguous() if dh_T is not None else torch.zeros(B, H, dtype=torch.float32, device=dev))
         if ctx.fast:
             w_hT = w_h_c.t().contiguous()
             dpre, dh0, dc0 = E.lstm_seq_bwd(dh_seq, w_hT, act, c_seq, dhT, dcT, _sync_ws(dev), SEQ_VARIANT)
@@ -174,7 +179,7 @@ class _LSTMSeqFn(torch.autograd.Function):
             STATS["kernels"] += 1
         else:
             dpre = torch.empty_like(act)
-            dh_rec: Optional[torch.Tensor] = None
+            dh_rec: Optional[torch.Tensor] = dhT if dh_T is not None else None
             dc = dcT
             for t in range(T - 1, -1, -1):
                 dp, dc = E.lstm_pointwise_bwd(dh_seq[t], dh_rec, dc, act[t], c_seq[t], c_seq[t + 1])
@@ -197,5 +202,4 @@ class _LSTMSeqFn(torch.autograd.Function):
 
 def lstm_layer_sequence(x_seq, h0, c0, w_x, w_h, bias):
     """``x_seq [T,B,D]`` (bf16 or fp32) -> ``(h_seq [T,B,H], h_T, c_T)``."""
-    h_seq, c_T = _LSTMSeqFn.apply(x_seq.contiguous(), h0, c0, w_x, w_h, bias)
-    return h_seq, h_seq[-1], c_T
+    return _LSTMSeqFn.apply(x_seq.contiguous(), h0, c0, w_x, w_h, bias)

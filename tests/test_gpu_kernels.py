@@ -94,7 +94,7 @@ def test_tcgen05_gemm(E, dev, variant, M, N, K):
     assert (Cb.float() - (R - bias)).abs().max() / R.abs().max() < 2e-2
 
 
-def _seq_case(dev, T, B, H, D, tol):
+def _seq_case(dev, T, B, H, D, tol, loss_on="seq"):
     from lstm_tensorspark_b200.ops import cuda_lstm
     ref = _ref()
     torch.manual_seed(1)
@@ -102,12 +102,19 @@ def _seq_case(dev, T, B, H, D, tol):
               torch.randn(4 * H, D, device=dev) / D ** 0.5, torch.randn(4 * H, H, device=dev) / H ** 0.5,
               torch.randn(4 * H, device=dev) * 0.1]
     pr = [p.bfloat16().float().requires_grad_(True) if i != 2 else p.clone().requires_grad_(True) for i, p in enumerate(params)]
-    hs_r, _, cT_r = ref.lstm_layer_sequence(*pr)
-    wgt = torch.randn_like(hs_r)
-    (hs_r * wgt).sum().backward()
+    hs_r, hT_r, cT_r = ref.lstm_layer_sequence(*pr)
+    wgt, w2, w3 = torch.randn_like(hs_r), torch.randn_like(hT_r), torch.randn_like(cT_r)
+
+    def loss(hs, hT, cT):
+        if loss_on == "last":            # only the final state is used downstream (top layer under the classifier): dh_seq is None
+            return (hT.float() * w2).sum()
+        if loss_on == "all":
+            return (hs.float() * wgt).sum() + (hT.float() * w2).sum() + (cT.float() * w3).sum()
+        return (hs.float() * wgt).sum()
+    loss(hs_r, hT_r, cT_r).backward()
     pc = [p.clone().requires_grad_(True) for p in params]
     hs, hT, cT = cuda_lstm.lstm_layer_sequence(pc[0].bfloat16(), pc[1], pc[2], pc[3], pc[4], pc[5])
-    (hs.float() * wgt).sum().backward()
+    loss(hs, hT, cT).backward()
     torch.cuda.synchronize()
     cuda_lstm.check_kernel_errors(dev)
     assert (hs.float() - hs_r).abs().max() < tol
@@ -123,6 +130,12 @@ def test_persistent_tcgen05_lstm_sequence(dev, T, B, H, D):
     n0 = cuda_lstm.STATS["fast_fwd"], cuda_lstm.STATS["fast_bwd"]
     _seq_case(dev, T, B, H, D, tol=3e-2)
     assert cuda_lstm.STATS["fast_fwd"] == n0[0] + 1 and cuda_lstm.STATS["fast_bwd"] == n0[1] + 1   # the tcgen05 path ran
+
+
+@pytest.mark.parametrize("loss_on", ["last", "all"])
+def test_persistent_lstm_final_state_gradients(dev, loss_on):
+    _seq_case(dev, 6, 200, 256, 128, tol=3e-2, loss_on=loss_on)
+    _seq_case(dev, 4, 20, 32, 16, tol=3e-2, loss_on=loss_on)          # generic path
 
 
 @pytest.mark.parametrize("T,B,H,D", [(1, 10, 16, 4), (6, 33, 48, 20)])
