@@ -158,18 +158,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               if (col + i < N) *reinterpret_cast<float4*>(dst + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
           } else {
             __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(Cout) + (size_t)row * N + col;
+            uint32_t pk[16];
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              if (col + i < N) {
-                uint4 pk;
-                __nv_bfloat162 p0 = __floats2bfloat162_rn(f[i], f[i + 1]);
-                __nv_bfloat162 p1 = __floats2bfloat162_rn(f[i + 2], f[i + 3]);
-                __nv_bfloat162 p2 = __floats2bfloat162_rn(f[i + 4], f[i + 5]);
-                __nv_bfloat162 p3 = __floats2bfloat162_rn(f[i + 6], f[i + 7]);
-                pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-                pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
-                *reinterpret_cast<uint4*>(dst + i) = pk;
-              }
+            for (int i = 0; i < 16; ++i) {
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+              pk[i] = *reinterpret_cast<uint32_t*>(&p2);
+            }
+            if ((N & 15) == 0 && col + 32 <= N) {
+              // whole 32 B sectors, 256-bit stores: half the L2 write requests of 16 B stores
+#pragma unroll
+              for (int i = 0; i < 2; ++i)
+                asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 16 * i), "r"(pk[8 * i]), "r"(pk[8 * i + 1]),
+                             "r"(pk[8 * i + 2]), "r"(pk[8 * i + 3]), "r"(pk[8 * i + 4]), "r"(pk[8 * i + 5]), "r"(pk[8 * i + 6]), "r"(pk[8 * i + 7]) : "memory");
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i += 8)
+                if (col + i < N) *reinterpret_cast<uint4*>(dst + i) = make_uint4(pk[i / 2], pk[i / 2 + 1], pk[i / 2 + 2], pk[i / 2 + 3]);
             }
           }
         }
