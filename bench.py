@@ -60,10 +60,23 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.rows = []          # (arrival time, csv line)
         self.proc = None
+        self.nvml = None
         self.gpu = gpu_index
         self.t_mark = None
 
     def start(self):
+        # NVML in-process (10 ms period: the timed region of a short run is ~100 ms); nvidia-smi -lms as the fallback
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.stop_evt = threading.Event()
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
@@ -72,6 +85,27 @@ class ClockSampler:
             self.t.start()
         except Exception:
             self.proc = None
+
+    def _poll_nvml(self):
+        n = self.nvml
+        bits = ((0x8, "Active"), (0x40, "Active"), (0x20, "Active"), (0x4, "Active"))     # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+        while not self.stop_evt.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+                try:
+                    mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                try:
+                    pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                except Exception:
+                    pw = 0.0
+                flags = ",".join(("Active" if mask & b else "Not Active") for b, _ in bits)
+                self.rows.append((time.time(), f"{self.gpu}, {sm}, {mx}, {pw:.1f}, {flags}"))
+            except Exception:
+                pass
+            self.stop_evt.wait(0.01)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -82,13 +116,17 @@ class ClockSampler:
         self.t_mark = time.time()
 
     def stop(self):
-        if self.proc is None:
+        if getattr(self, "nvml", None) is not None:
+            self.stop_evt.set()
+            self.t.join(1.0)
+        elif self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(2)
-        except Exception:
-            pass
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(2)
+            except Exception:
+                pass
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         timed = [r for (t, r) in self.rows if self.t_mark is None or t >= self.t_mark]

@@ -133,10 +133,29 @@ def dump_sass(out_dir: str) -> List[str]:
         r = subprocess.run([os.path.join(_cuda_home(), "bin", "cuobjdump"), "-sass", obj], stdout=subprocess.PIPE,
                            stderr=subprocess.STDOUT, text=True)
         p = os.path.join(out_dir, os.path.basename(cu)[:-3] + ".sass")
+        text = r.stdout
+        keep = SASS_KEEP.get(os.path.basename(cu))
+        if keep:
+            text = _filter_sass(text, keep)
         with open(p, "w") as f:
-            f.write(r.stdout)
+            f.write(text)
         outs.append(p)
     return outs
+
+
+# lstm_seq_tcgen05.cu has ~30 template instantiations (ring depths, tuning variants): the committed listing keeps the
+# ones that run by default (forward K-split 5-stage, backward 5-stage, streamed-weights 8-stage, prologue).
+SASS_KEEP = {"lstm_seq_tcgen05.cu": ("ILb0ELi5ELi1ELb0ELb1E", "ILb1ELi5ELi1ELb0ELb0E", "ILb0ELi8ELi1ELb1ELb0E", "seq_prologue_kernel")}
+
+
+def _filter_sass(text: str, keep) -> str:
+    parts = text.split("\t\tFunction : ")
+    out = [parts[0]]
+    for part in parts[1:]:
+        name = part.split("\n", 1)[0]
+        if any(k in name for k in keep):
+            out.append(part)
+    return "\t\tFunction : ".join(out)
 
 
 def ptxas_report() -> str:

@@ -50,6 +50,7 @@ constexpr int kABytes = BM * BK * 2;          // 16 KB
 constexpr int kWBlockBytes = BN * BK * 2;     // 8 KB per 64-wide K block
 constexpr int kXchgBytes = 4 * BM * 16 * 2;   // backward: 4 source slots of [128 x 16] bf16 partial chunks
 constexpr long long kSpinLimit = 6000000000LL;   // ~3 s of SM clocks: a bug surfaces as an error, not a hung GPU
+constexpr long long kAbortGrace = 1000000000LL;  // ~0.5 s for the role loops to drain after an abort before the watchdog traps
 
 // sync workspace (u32 words): [0,16) grid-barrier counters, [64,320) per-CTA step flags, [512 + 32 i) k-block arrival
 // counters (one 128 B line each, i < tiles_m * 4H/64 <= 148 + ...), [kSyncWords-1] sticky error flag
@@ -68,6 +69,7 @@ struct SeqSmem {
   uint64_t xchg_free[2];        // every cluster member has consumed its exchange buffer of the previous step (4 remote arrivals)
   uint32_t tmem_slot;
   int abort_flag;
+  int roles_done;               // role warps that have left their loops (producer, MMA issuer, 8 epilogue warps)
   uint32_t kb_idx[kMaxStages];  // which k-block sits in ring stage s (the producer fills stages in ARRIVAL order)
   float bias[64];
 };
@@ -271,6 +273,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
 
   if (threadIdx.x == 0) {
     ss->abort_flag = 0;
+    ss->roles_done = 0;
     tc::prefetch_tmap(&tmap_w);
     for (int s = 0; s < kStages; ++s) { tc::mbar_init(&ss->full[s], 1); tc::mbar_init(&ss->empty[s], 1); }
     tc::mbar_init(&ss->w_full, 1);
@@ -432,6 +435,8 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
         }
       }
     }
+    __syncwarp();
+    if (lane == 0) atomicAdd(&ss->roles_done, 1);
   } else if (warp == 1) {
     // ======================================================================== MMA issuer
     constexpr uint32_t idesc = tc::make_idesc_bf16_f32(BM, kBNm);
@@ -508,6 +513,25 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
      }
       if (prof && lane == 0) {           // [first-turn wait (incl. grid barrier + first loads), later waits, whole step] in cycles
         p.dbg[4 * s + 3] = (unsigned long long)t_first | ((unsigned long long)t_wait << 20) | ((unsigned long long)(clock64() - t_begin) << 40);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) atomicAdd(&ss->roles_done, 1);
+  } else if (warp == 3) {
+    // ======================================================================== watchdog
+    // A bounded spin that times out raises abort_flag and every role loop drains.  A thread already parked in a named
+    // barrier (bar.sync cannot time out) would keep the grid alive forever: if the roles have not all left within the
+    // grace period after an abort, kill the kernel (launch failure in the host process) instead of hanging the GPU.
+    long long t_abort = 0;
+    while (*reinterpret_cast<volatile int*>(&ss->roles_done) < 10) {
+      __nanosleep(4000);
+      if (*abort_flag) {
+        if (t_abort == 0) t_abort = clock64();
+        else if (clock64() - t_abort > kAbortGrace) {
+          if (lane == 0) atomicExch(reinterpret_cast<int*>(p.sync + kSyncErr), 2);
+          __threadfence_system();
+          __trap();
+        }
       }
     }
   } else if (warp >= kEpiWarp0) {
@@ -819,6 +843,10 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
     }
   }
 
+  if (warp >= kEpiWarp0) {
+    __syncwarp();
+    if (lane == 0) atomicAdd(&ss->roles_done, 1);
+  }
   tc::fence_before_sync();
   __syncthreads();
   if (kCluster) cluster_sync_all();              // nobody exits while a peer may still write into / arrive on its smem
