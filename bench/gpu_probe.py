@@ -192,7 +192,7 @@ def check_seq_tune():
             v = tiles + 16 * st + 4096 * mode + 65536 * sync + 262144 * acq + 524288 * nosplit
             try:
                 ms = _time_ms(lambda: E.lstm_seq_fwd(gx, whb, bias, h0, c0, ws, v), iters=5, warm=2)
-                dbg = torch.zeros(4 * (T + 2) + 64, dtype=torch.int64, device=dev)
+                dbg = torch.zeros(4 * (T + 2) + 64 + 512, dtype=torch.int64, device=dev)
                 E.lstm_seq_fwd(gx, whb, bias, h0, c0, ws, v, dbg)
                 torch.cuda.synchronize()
                 cuda_lstm.check_kernel_errors(dev)
@@ -217,6 +217,47 @@ def check_seq_tune():
                       accum_ns=int(d[0, 1]) - t0)
             except Exception as e:                     # noqa: BLE001
                 _emit("fwd_variant", T=T, B=B, H=H, tiles=tiles, stages=st, error=repr(e)[:300])
+
+
+def check_bwd_tune():
+    """Backward kernel: per-phase timestamps of CTA 0 (first operand block ready / accumulator ready / signalled)."""
+    import torch
+    from lstm_tensorspark_b200.ops import cuda_lstm
+    from lstm_tensorspark_b200.ops.cuda_ext import ext
+    E = ext()
+    dev = torch.device("cuda")
+    T, B, H = 128, 256, 1024
+    torch.manual_seed(0)
+    gx = (torch.randn(T, B, 4 * H, device=dev) * 0.5).bfloat16()
+    whb = (torch.randn(4 * H, H, device=dev) / H ** 0.5).bfloat16()
+    bias = torch.zeros(4 * H, device=dev)
+    h0 = torch.zeros(B, H, device=dev).bfloat16(); c0 = torch.zeros(B, H, device=dev)
+    ws = cuda_lstm._sync_ws(dev)
+    h_seq, c_seq, act = E.lstm_seq_fwd(gx, whb, bias, h0, c0, ws, 0)
+    dh_seq = (torch.randn(T, B, H, device=dev) * 0.1).bfloat16()
+    w_hT = whb.t().contiguous()
+    z = torch.zeros(B, H, device=dev)
+    for (mode, sync) in ((0, 0), (0, 1), (1, 0), (2, 0)):
+        v = 4096 * mode + 65536 * sync
+        try:
+            ms = _time_ms(lambda: E.lstm_seq_bwd(dh_seq, w_hT, act, c_seq, z, z, ws, v), iters=5, warm=2)
+            dbg = torch.zeros(4 * (T + 2) + 64 + 512, dtype=torch.int64, device=dev)
+            E.lstm_seq_bwd(dh_seq, w_hT, act, c_seq, z, z, ws, v, dbg)
+            torch.cuda.synchronize()
+            cuda_lstm.check_kernel_errors(dev)
+            d = dbg[:4 * (T + 2)].view(-1, 4)[8:40].cpu()
+            waited, accum, sig = d[:, 0], d[:, 1], d[:, 2]
+            w3 = d[:, 3]
+            mma_first = [int(x) & 0xFFFFF for x in w3]
+            mma_wait = [(int(x) >> 20) & 0xFFFFF for x in w3]
+            mma_total = [(int(x) >> 40) & 0xFFFFF for x in w3]
+            n = len(mma_first)
+            _emit("bwd_variant", debug_mode=mode, sync=sync, us_per_step=ms * 1e3 / (T + 1),
+                  mma_first_wait_us=sum(mma_first) / n / 1965, mma_later_wait_us=sum(mma_wait) / n / 1965, mma_step_us=sum(mma_total) / n / 1965,
+                  load_mma_us=float((accum - waited).float().mean()) / 1e3, epi_us=float((sig - accum).float().mean()) / 1e3,
+                  sync_us=float((waited[1:] - sig[:-1]).float().mean()) / 1e3)
+        except Exception as e:                     # noqa: BLE001
+            _emit("bwd_variant", debug_mode=mode, sync=sync, error=repr(e)[:300])
 
 
 def check_skew():
@@ -317,7 +358,7 @@ def check_iris_gpu():
     _emit("iris_gpu_standalone", rc=r.returncode, tail=(r.stdout + r.stderr)[-600:])
 
 
-CHECKS = {"seq_h2048": check_seq_h2048, "skew": check_skew, "seq_tiles": check_seq_tiles, "umma": check_umma, "seq_tune": check_seq_tune, "env": check_env, "simple": check_simple, "gemm": check_gemm, "generic": check_generic, "seq_small": check_seq_small,
+CHECKS = {"seq_h2048": check_seq_h2048, "bwd_tune": check_bwd_tune, "skew": check_skew, "seq_tiles": check_seq_tiles, "umma": check_umma, "seq_tune": check_seq_tune, "env": check_env, "simple": check_simple, "gemm": check_gemm, "generic": check_generic, "seq_small": check_seq_small,
           "seq_big": check_seq_big, "engine": check_engine, "iris_gpu": check_iris_gpu}
 
 
