@@ -15,6 +15,8 @@ using torch::Tensor;
 
 extern "C" {
 int ts_lstm_pointwise_fwd(const void*, const float*, const float*, void*, float*, void*, int, int, int, cudaStream_t);
+int ts_transpose01_rows(const void*, void*, int, int, long long, cudaStream_t);
+int ts_lstm_seq_cluster_probe(int);
 int ts_lstm_pointwise_bwd(const void*, const float*, const float*, const void*, const float*, const float*, void*,
                           float*, int, int, int, cudaStream_t);
 int ts_head_xent(const void*, const float*, const float*, const long long*, float*, float*, float*, int*, int, int, int,
@@ -59,6 +61,19 @@ int is_bf16(const Tensor& t) {
   return t.scalar_type() == torch::kBFloat16 ? 1 : 0;
 }
 const float* fptr(const std::optional<Tensor>& t) { return t.has_value() ? t->data_ptr<float>() : nullptr; }
+
+// x [B,T,D] contiguous -> [T,B,D] contiguous (row permutation at copy speed)
+Tensor transpose01(const Tensor& x) {
+  chk_cuda(x, "x");
+  TORCH_CHECK(x.dim() == 3 && x.is_contiguous(), "transpose01: expected a contiguous [B,T,D] tensor");
+  c10::cuda::CUDAGuard g(x.device());
+  const int B = x.size(0), T = x.size(1);
+  const long long row_bytes = (long long)x.size(2) * x.element_size();
+  TORCH_CHECK(row_bytes % 16 == 0, "transpose01: row size must be a multiple of 16 bytes");
+  auto out = torch::empty({x.size(1), x.size(0), x.size(2)}, x.options());
+  check(ts_transpose01_rows(x.data_ptr(), out.data_ptr(), B, T, row_bytes, stream()), "transpose01");
+  return out;
+}
 
 // ---- generic LSTM cell epilogue -------------------------------------------------------------------------
 std::vector<Tensor> lstm_pointwise_fwd(const Tensor& pre, const Tensor& bias, const Tensor& c_prev) {
@@ -231,6 +246,8 @@ Tensor umma_bench(int64_t M, int64_t N, int64_t iters, int64_t mode) {
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "lstm_tensorspark_b200 sm_100a kernels";
   m.def("lstm_pointwise_fwd", &lstm_pointwise_fwd);
+  m.def("transpose01", &transpose01);
+  m.def("lstm_seq_cluster_probe", [](int64_t c) { return ts_lstm_seq_cluster_probe((int)c); });
   m.def("lstm_pointwise_bwd", &lstm_pointwise_bwd);
   m.def("head_xent", &head_xent);
   m.def("xent_rows", &xent_rows);

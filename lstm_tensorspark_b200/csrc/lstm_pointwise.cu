@@ -89,3 +89,29 @@ extern "C" int ts_lstm_pointwise_bwd(const void* dh_a, const float* dh_b, const 
                                                                   c_prev, c_new, (float*)dpre, dc_out, B, H);
   return (int)cudaGetLastError();
 }
+
+
+// [B,T,D] -> [T,B,D] for a row-contiguous tensor (row = D elements, row_bytes % 16 == 0): a pure row permutation, so it
+// runs at copy speed with 16 B vectors (the framework's generic strided copy of the transposed view takes 3.5x longer).
+// Replaces the batch-major -> time-major feed conversion in front of the first layer's x-projection GEMM.
+namespace {
+__global__ void transpose01_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B, int T, int vec_per_row) {
+  const long long total = (long long)B * T * vec_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / vec_per_row;          // destination row = t * B + b
+    const int v = (int)(i - row * vec_per_row);
+    const int t = (int)(row / B), b = (int)(row - (long long)t * B);
+    dst[i] = src[((long long)b * T + t) * vec_per_row + v];
+  }
+}
+}  // namespace
+
+extern "C" int ts_transpose01_rows(const void* src, void* dst, int B, int T, long long row_bytes, cudaStream_t st) {
+  if (row_bytes % 16 != 0) return -2;
+  const int vec = (int)(row_bytes / 16);
+  const long long total = (long long)B * T * vec;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  transpose01_rows_kernel<<<blocks, 256, 0, st>>>((const uint4*)src, (uint4*)dst, B, T, vec);
+  return (int)cudaGetLastError();
+}

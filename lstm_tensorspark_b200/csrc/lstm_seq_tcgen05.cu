@@ -1029,3 +1029,23 @@ extern "C" int ts_lstm_seq_bwd(const void* dh_seq, const void* w_hT, const void*
   p.dh0 = dh0; p.dc0 = dc0; p.sync = sync_ws; p.T = T; p.B = B; p.H = H; p.dbg = (unsigned long long*)dbg;
   return seq_common<true>(p, w_hT, variant, st);
 }
+
+
+// Feasibility probe: how many clusters of `cluster` CTAs of the backward kernel (1 CTA/SM, ~226 KB smem) can be co-resident.
+// Measured on B200: 1 -> 148, 2 -> 74, 4 -> 33, 8 -> 15, 16 -> 7: an 8-way backward K-split (N = 128, 8 k-blocks per step,
+// the mirror of the forward 2-way split) would need 16 clusters of 8 at B = 256, H = 1024 and is therefore not launchable.
+extern "C" int ts_lstm_seq_cluster_probe(int cluster) {
+  auto kern = lstm_seq_kernel<true, 4, 1, false, false>;
+  const size_t smem = 226 * 1024;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return -1; }
+  if (cluster > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return -2; }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(128 / cluster * cluster); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = smem; cfg.stream = 0;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return -3; }
+  return n;
+}

@@ -151,6 +151,7 @@ class _LSTMSeqFn(torch.autograd.Function):
             STATS["generic_fwd"] += 1
             STATS["kernels"] += T
         ctx.save_for_backward(x2d, h_seq, c_seq, act, w_x_c, w_h_c)
+        ctx.set_materialize_grads(False)       # an unused output must arrive as None, not as a zero-filled [T,B,H] tensor
         ctx.fast = fast
         ctx.dims = (T, B, D, H)
         ctx.w_addrs = (w_x.data_ptr(), w_h.data_ptr())
@@ -202,4 +203,8 @@ class _LSTMSeqFn(torch.autograd.Function):
 
 def lstm_layer_sequence(x_seq, h0, c0, w_x, w_h, bias):
     """``x_seq [T,B,D]`` (bf16 or fp32) -> ``(h_seq [T,B,H], h_T, c_T)``."""
+    if (not x_seq.is_contiguous() and not x_seq.requires_grad and x_seq.transpose(0, 1).is_contiguous()
+            and (x_seq.shape[2] * x_seq.element_size()) % 16 == 0):
+        x_seq = ext().transpose01(x_seq.transpose(0, 1))     # batch-major feed -> time-major, a row permutation at copy speed
+        STATS["kernels"] += 1
     return _LSTMSeqFn.apply(x_seq.contiguous(), h0, c0, w_x, w_h, bias)

@@ -132,6 +132,14 @@ def test_persistent_tcgen05_lstm_sequence(dev, T, B, H, D):
     assert cuda_lstm.STATS["fast_fwd"] == n0[0] + 1 and cuda_lstm.STATS["fast_bwd"] == n0[1] + 1   # the tcgen05 path ran
 
 
+def test_transpose01_rows(dev):
+    from lstm_tensorspark_b200.ops.cuda_ext import ext
+    for (B, T, D, dt) in ((7, 5, 24, torch.bfloat16), (64, 33, 1024, torch.bfloat16), (3, 4, 8, torch.float32)):
+        x = torch.randn(B, T, D, device=dev).to(dt)
+        y = ext().transpose01(x)
+        assert y.shape == (T, B, D) and torch.equal(y, x.transpose(0, 1).contiguous())
+
+
 @pytest.mark.parametrize("loss_on", ["last", "all"])
 def test_persistent_lstm_final_state_gradients(dev, loss_on):
     _seq_case(dev, 6, 200, 256, 128, tol=3e-2, loss_on=loss_on)
