@@ -17,6 +17,8 @@ extern "C" {
 int ts_lstm_pointwise_fwd(const void*, const float*, const float*, void*, float*, void*, int, int, int, cudaStream_t);
 int ts_transpose01_rows(const void*, void*, int, int, long long, cudaStream_t);
 int ts_lstm_seq_cluster_probe(int);
+int ts_transpose2d_b16(const void*, void*, int, int, cudaStream_t);
+int ts_colsum_bf16(const void*, float*, int, int, cudaStream_t);
 int ts_lstm_pointwise_bwd(const void*, const float*, const float*, const void*, const float*, const float*, void*,
                           float*, int, int, int, cudaStream_t);
 int ts_head_xent(const void*, const float*, const float*, const long long*, float*, float*, float*, int*, int, int, int,
@@ -72,6 +74,26 @@ Tensor transpose01(const Tensor& x) {
   TORCH_CHECK(row_bytes % 16 == 0, "transpose01: row size must be a multiple of 16 bytes");
   auto out = torch::empty({x.size(1), x.size(0), x.size(2)}, x.options());
   check(ts_transpose01_rows(x.data_ptr(), out.data_ptr(), B, T, row_bytes, stream()), "transpose01");
+  return out;
+}
+
+// [R,C] bf16/fp16 contiguous -> [C,R] contiguous (shared-memory tile transpose)
+Tensor transpose2d(const Tensor& x) {
+  chk_cuda(x, "x");
+  TORCH_CHECK(x.dim() == 2 && x.is_contiguous() && x.element_size() == 2, "transpose2d: expected a contiguous 2-D 16-bit tensor");
+  c10::cuda::CUDAGuard g(x.device());
+  auto out = torch::empty({x.size(1), x.size(0)}, x.options());
+  check(ts_transpose2d_b16(x.data_ptr(), out.data_ptr(), (int)x.size(0), (int)x.size(1), stream()), "transpose2d");
+  return out;
+}
+
+// column sums of a contiguous bf16 [rows, cols] matrix -> fp32 [cols]
+Tensor colsum_bf16(const Tensor& x) {
+  chk_cuda(x, "x");
+  TORCH_CHECK(x.dim() == 2 && x.is_contiguous() && is_bf16(x) && x.size(1) % 256 == 0, "colsum_bf16: contiguous bf16 [rows, cols], cols % 256 == 0");
+  c10::cuda::CUDAGuard g(x.device());
+  auto out = torch::zeros({x.size(1)}, x.options().dtype(torch::kFloat32));
+  check(ts_colsum_bf16(x.data_ptr(), out.data_ptr<float>(), (int)x.size(0), (int)x.size(1), stream()), "colsum_bf16");
   return out;
 }
 
@@ -247,6 +269,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "lstm_tensorspark_b200 sm_100a kernels";
   m.def("lstm_pointwise_fwd", &lstm_pointwise_fwd);
   m.def("transpose01", &transpose01);
+  m.def("transpose2d", &transpose2d);
+  m.def("colsum_bf16", &colsum_bf16);
   m.def("lstm_seq_cluster_probe", [](int64_t c) { return ts_lstm_seq_cluster_probe((int)c); });
   m.def("lstm_pointwise_bwd", &lstm_pointwise_bwd);
   m.def("head_xent", &head_xent);

@@ -107,6 +107,14 @@ def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         return (a @ b).float()
 
 
+def _transposed(w: torch.Tensor) -> torch.Tensor:
+    """``w [R,C]`` -> contiguous ``[C,R]`` (tile-transpose kernel for 16-bit CUDA tensors)."""
+    if w.is_cuda and w.dim() == 2 and w.element_size() == 2 and w.is_contiguous():
+        STATS["kernels"] += 1
+        return ext().transpose2d(w)
+    return w.t().contiguous()
+
+
 def _gemm_tn(a: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     """a [M,K] @ w[N,K]^T -> [M,N] in a.dtype; tcgen05 kernel when bf16 and aligned, library GEMM otherwise."""
     if USE_TC_GEMM and a.dtype == torch.bfloat16 and a.shape[1] % 8 == 0 and w.shape[0] % 8 == 0 and a.shape[0] >= 128:
@@ -174,7 +182,7 @@ class _LSTMSeqFn(torch.autograd.Function):
         dcT = (dc_T.float().contiguous() if dc_T is not None else torch.zeros(B, H, dtype=torch.float32, device=dev))
         dhT = (dh_T.float().contiguous() if dh_T is not None else torch.zeros(B, H, dtype=torch.float32, device=dev))
         if ctx.fast:
-            w_hT = w_h_c.t().contiguous()
+            w_hT = _transposed(w_h_c)
             dpre, dh0, dc0 = E.lstm_seq_bwd(dh_seq, w_hT, act, c_seq, dhT, dcT, _sync_ws(dev), SEQ_VARIANT)
             STATS["fast_bwd"] += 1
             STATS["kernels"] += 1
@@ -193,10 +201,14 @@ class _LSTMSeqFn(torch.autograd.Function):
         dg_t = dg2d.t()
         dw_x = _accumulate_grad(ctx.w_addrs[0], dg_t, x2d)
         dw_h = _accumulate_grad(ctx.w_addrs[1], dg_t, h_seq[:T].reshape(T * B, H))
-        db = torch.sum(dg2d, dim=0, dtype=torch.float32)
+        if dg2d.is_cuda and dg2d.dtype == torch.bfloat16 and dg2d.shape[1] % 256 == 0 and dg2d.is_contiguous():
+            db = E.colsum_bf16(dg2d)
+            STATS["kernels"] += 1
+        else:
+            db = torch.sum(dg2d, dim=0, dtype=torch.float32)
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = _gemm_tn(dg2d, w_x_c.t().contiguous()).view(T, B, D) if cd == torch.bfloat16 else (dg2d @ w_x_c).view(T, B, D)
+            dx = _gemm_tn(dg2d, _transposed(w_x_c)).view(T, B, D) if cd == torch.bfloat16 else (dg2d @ w_x_c).view(T, B, D)
         h0_dt, c0_dt = ctx.in_dtypes
         return dx, dh0.to(h0_dt), dc0.to(c0_dt), dw_x, dw_h, db
 

@@ -132,6 +132,22 @@ def test_persistent_tcgen05_lstm_sequence(dev, T, B, H, D):
     assert cuda_lstm.STATS["fast_fwd"] == n0[0] + 1 and cuda_lstm.STATS["fast_bwd"] == n0[1] + 1   # the tcgen05 path ran
 
 
+def test_colsum_bf16(dev):
+    from lstm_tensorspark_b200.ops.cuda_ext import ext
+    for (R, C) in ((1000, 256), (32768, 4096), (7, 512)):
+        x = (torch.randn(R, C, device=dev) * 0.3).bfloat16()
+        ref = x.float().sum(0)
+        got = ext().colsum_bf16(x)
+        assert (got - ref).abs().max() <= 1e-3 * max(1.0, float(ref.abs().max()))
+
+
+def test_transpose2d(dev):
+    from lstm_tensorspark_b200.ops.cuda_ext import ext
+    for (R, C) in ((4096, 1024), (1024, 4096), (100, 36), (65, 129)):
+        x = torch.randn(R, C, device=dev).bfloat16()
+        assert torch.equal(ext().transpose2d(x), x.t().contiguous())
+
+
 def test_transpose01_rows(dev):
     from lstm_tensorspark_b200.ops.cuda_ext import ext
     for (B, T, D, dt) in ((7, 5, 24, torch.bfloat16), (64, 33, 1024, torch.bfloat16), (3, 4, 8, torch.float32)):
