@@ -24,7 +24,7 @@ from .comm import TorchDistComm
 MODE_AVG, MODE_SGD, MODE_ADAM = 0, 1, 2
 TWO_SHOT_BYTES = int(os.environ.get("LSTM_TS_AR_TWO_SHOT_BYTES", str(32 * 1024)))     # measured: two-shot wins from ~16 KB up (profiles/)
 AR_BLOCKS = int(os.environ.get("LSTM_TS_AR_BLOCKS", "64"))
-AR_BLOCKS_LARGE = int(os.environ.get("LSTM_TS_AR_BLOCKS_LARGE", "128"))   # messages >= 32 MB
+AR_BLOCKS_LARGE = int(os.environ.get("LSTM_TS_AR_BLOCKS_LARGE", "64"))    # messages >= 32 MB (measured: 64 = 128 = 256 blocks, unroll irrelevant: sweep8c.log)
 
 
 def _align(x: int, a: int = 4096) -> int:
