@@ -62,15 +62,13 @@ def main():
         if comm.arena.mc_base:
             variants.append(("two_shot_nvls", "two_shot", "auto", 0, False))
             if tune and size >= (1 << 22):
-                variants += [("nvls_b64", "two_shot", "auto", 64, False), ("nvls_b64_u4", "two_shot", "auto", 64, True),
-                             ("nvls_b128", "two_shot", "auto", 128, False), ("nvls_b128_u4", "two_shot", "auto", 128, True),
+                variants += [("nvls_b64", "two_shot", "auto", 64, False), ("nvls_b128", "two_shot", "auto", 128, False),
                              ("nvls_b256", "two_shot", "auto", 256, False)]
         for name, force, mc, blocks, unroll in variants:
             if force == "one_shot" and size > (1 << 26):
                 continue
             comm.use_multicast = mc
             comm.blocks_override = blocks
-            comm.mc_unroll = unroll
 
             def fn():
                 comm._launch(0, comm.off_data, n, force=force)

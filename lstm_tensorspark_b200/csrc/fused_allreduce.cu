@@ -145,7 +145,7 @@ TS_DEVICE float effective_lr(const ARArgs& a) {
 }
 __global__ void ar_inc_step_kernel(int* step) { *step += 1; }
 
-template <int kMode, bool kMulticast, bool kUnroll = false>
+template <int kMode, bool kMulticast>
 __global__ void __launch_bounds__(kThreads) ar_two_shot_kernel(const __grid_constant__ ARArgs a) {
   const float lr = kMode == MODE_ADAM ? effective_lr(a) : a.lr;
   uint32_t epoch = a.epochs[blockIdx.x];
@@ -155,24 +155,6 @@ __global__ void __launch_bounds__(kThreads) ar_two_shot_kernel(const __grid_cons
   long long lo = per * a.rank, hi = lo + per < a.n4 ? lo + per : a.n4;
   long long stride = (long long)gridDim.x * kThreads;
   long long i = lo + (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (kMulticast && kUnroll) {
-    // 4 independent switch reductions in flight per thread (NVLink round trips are ~2 us: memory-level parallelism,
-    // not thread count, sets the bandwidth of the large-message regime)
-    for (; i + 3 * stride < hi; i += 4 * stride) {
-      float4 s4[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) s4[u] = mc_ld_reduce_f4(a.mc_in + 4 * (i + u * stride));
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const long long j = i + u * stride;
-        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kMode != MODE_AVG) w = reinterpret_cast<const float4*>(a.param[a.rank])[j];
-        const float4 nw = apply_update<kMode>(a, s4[u], j, w, lr);
-        mc_st_f4(a.mc_param + 4 * j, nw);
-        if (a.mc_shadow) mc_st_bf16x4(a.mc_shadow + 4 * j, pack_bf16x4(nw));
-      }
-    }
-  }
   for (; i < hi; i += stride) {
     float4 sum;
     if (kMulticast) {
@@ -244,8 +226,7 @@ __global__ void __launch_bounds__(kThreads) ar_one_shot_kernel(const __grid_cons
 template <int kMode>
 int launch_mode(const ARArgs& a, int two_shot, int multicast, int blocks, cudaStream_t st) {
   if (two_shot) {
-    if (multicast == 2) ar_two_shot_kernel<kMode, true, true><<<blocks, kThreads, 0, st>>>(a);   // 4 switch reductions in flight per thread
-    else if (multicast) ar_two_shot_kernel<kMode, true><<<blocks, kThreads, 0, st>>>(a);
+    if (multicast) ar_two_shot_kernel<kMode, true><<<blocks, kThreads, 0, st>>>(a);
     else ar_two_shot_kernel<kMode, false><<<blocks, kThreads, 0, st>>>(a);
   } else {
     ar_one_shot_kernel<kMode><<<blocks, kThreads, 0, st>>>(a);

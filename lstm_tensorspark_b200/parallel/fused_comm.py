@@ -81,8 +81,7 @@ class FusedComm(TorchDistComm):
         self.timeout_s = timeout_s
         self.arena: Optional[SymmetricArena] = None
         self.use_multicast = os.environ.get("LSTM_TS_AR_MULTICAST", "auto")
-        self.mc_unroll = os.environ.get("LSTM_TS_AR_UNROLL", "0") == "1"      # tuning knobs (bench/allreduce_sweep.py)
-        self.blocks_override = 0
+        self.blocks_override = 0          # tuning knob (bench/allreduce_sweep.py)
         self.launches = 0
 
     # ------------------------------------------------------------------------------------------------
@@ -132,7 +131,7 @@ class FusedComm(TorchDistComm):
         ptrs = self._ptr_table(off_in_eff)
         E.fused_allreduce(ptrs, A.mc(off_in_eff) if mc else 0, A.mc(self.off_data) if mc else 0,
                           A.mc(self.off_shadow) if mc else 0, m, v, self.epochs, self.err, n, self.rank, self.world_size,
-                          mode, two_shot, (2 if self.mc_unroll else 1) if mc else 0,
+                          mode, two_shot, mc,
                           self.blocks_override or (AR_BLOCKS_LARGE if 4 * n >= (32 << 20) else AR_BLOCKS), lr, b1, b2, eps, wd,
                           float(self.timeout_s), step_dev)
         self.launches += 1
