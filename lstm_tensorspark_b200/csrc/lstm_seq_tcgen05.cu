@@ -84,20 +84,11 @@ TC_DEVICE uint32_t mapa(uint32_t local_smem_addr, uint32_t cta) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta));
   return r;
 }
-TC_DEVICE void st_cluster_f4(uint32_t addr, float4 v) {
-  asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-TC_DEVICE void st_cluster_u4(uint32_t addr, uint4 v) {
-  asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
 // 16 B into a cluster member's shared memory; the bytes are accounted on ITS mbarrier (complete_tx), so the receiver needs
 // no release/acquire round trip: it arms the barrier with expect_tx and waits, exactly as for a TMA load.
 TC_DEVICE void st_async_u4(uint32_t remote_addr, uint4 v, uint32_t remote_bar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];"
                ::"r"(remote_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(remote_bar) : "memory");
-}
-TC_DEVICE void mbar_arrive_remote(uint32_t remote_bar_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
 }
 // "Buffer consumed" notifications carry no data: the reads they order were complete (their values used) before the CTA
 // barrier that precedes the arrive.  The .release form compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR - a second
@@ -113,15 +104,6 @@ TC_DEVICE bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok) : "r"(tc::smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
-}
-TC_DEVICE void tma_load_3d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(tc::smem_u32(smem_dst)), "l"((uint64_t)map), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
-}
-TC_DEVICE void mma_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(tc::smem_u32(bar)), "h"(mask) : "memory");
 }
 
 template <bool kClusterScope>
@@ -139,19 +121,6 @@ TC_DEVICE bool wait_bar(uint64_t* bar, uint32_t parity, volatile int* abort_flag
   return true;
 }
 
-TC_DEVICE bool wait_counter(const unsigned int* ctr, unsigned int target, volatile int* abort_flag) {
-  long long t0 = clock64();
-  int n = 0;
-  while (true) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-    if ((int)(v - target) >= 0) return true;
-    if ((++n & 63) == 0) {
-      if (*abort_flag) return false;
-      if (clock64() - t0 > kSpinLimit) { *abort_flag = 1; return false; }
-    }
-  }
-}
 TC_DEVICE unsigned int ld_acquire_gpu(const unsigned int* ctr) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
@@ -546,6 +515,12 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
     bool ok = true;
     const bool dbg_thread = p.dbg && blockIdx.x == 0 && etid == 0;
     auto epi_bar = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    // exchange-buffer barriers: filled by st.async (async proxy, like a TMA load) / freed by relaxed arrives, so a CTA-scope
+    // wait is enough; the cluster-scope acquire form (debug_mode 7, the earlier default) adds a CCTL.IVALL per wait
+    const bool cluster_acquire = p.debug_mode == 7;
+    auto xwait = [&](uint64_t* bar, uint32_t parity, volatile int* af) {
+      return cluster_acquire ? wait_bar<true>(bar, parity, af) : wait_bar<false>(bar, parity, af);
+    };
     // MEMBAR.ALL.GPU (the release of the dataflow signal) drains EVERY outstanding store of the SM, not just the signalling
     // thread's: if the other 255 threads start their 57 KB of bookkeeping stores (h_seq / c_seq / activations) meanwhile, the
     // signal - the only thing the other CTAs wait for - is held back by 1-3 us (measured).  They wait for it instead.
@@ -600,7 +575,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&ss->tmem_empty[tile]);     // the issuer may overwrite the accumulator
             if (t > 0) {                                               // the peer has consumed last step's partial
-              ok = wait_bar<true>(&ss->xchg_free[0], (uint32_t)((t - 1) & 1), abort_flag);
+              ok = xwait(&ss->xchg_free[0], (uint32_t)((t - 1) & 1), abort_flag);
               if (!ok) break;
             }
             const uint32_t drow = mapa(xbase + (uint32_t)(rloc * 128), (uint32_t)(1 - ks));
@@ -611,7 +586,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
               for (int k = 0; k < 4; ++k) pk[k] = pack_bf2(__uint_as_float(u[8 * i + 2 * k]), __uint_as_float(u[8 * i + 2 * k + 1]));
               st_async_u4(drow + (uint32_t)((((4 * half + i) ^ (rloc & 7))) * 16), make_uint4(pk[0], pk[1], pk[2], pk[3]), pbar);
             }
-            ok = wait_bar<true>(&ss->xchg_full[0], xphase, abort_flag);
+            ok = xwait(&ss->xchg_full[0], xphase, abort_flag);
             if (!ok) break;
             xphase ^= 1;
 #pragma unroll
@@ -750,7 +725,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
             // A member only needs the dG blocks of ITS K-quarter, so nothing in the dataflow stops a fast member from being a
             // whole step ahead of a slow one: explicit back-pressure before overwriting anybody's exchange buffer.
             if (s > 1) {
-              ok = wait_bar<true>(&ss->xchg_free[tile], (uint32_t)(s & 1), abort_flag);
+              ok = xwait(&ss->xchg_free[tile], (uint32_t)(s & 1), abort_flag);
               if (!ok) break;
             }
             // reduce-scatter over the 4 K-quarters: column chunk q (16 wide, bf16) goes to member q's slot [ks] (DSMEM)
@@ -764,7 +739,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
               st_async_u4(dst, make_uint4(pk[0], pk[1], pk[2], pk[3]), dbar);
               st_async_u4(dst + 16, make_uint4(pk[4], pk[5], pk[6], pk[7]), dbar);
             }
-            ok = wait_bar<true>(&ss->xchg_full[tile], xphase, abort_flag);
+            ok = xwait(&ss->xchg_full[tile], xphase, abort_flag);
             if (!ok) break;
 #pragma unroll
             for (int i = 0; i < 8; ++i) dh[tile][i] = 0.f;

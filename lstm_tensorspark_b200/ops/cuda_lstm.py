@@ -1,8 +1,8 @@
 """CUDA LSTM layer op = autograd.Function around the hand-written kernels.
 
-Fast path (bf16, H % 64 == 0, weight slice fits in SMEM, grid <= #SMs): hoisted input projection on the tcgen05
-GEMM (csrc/gemm_tcgen05.cu) + ONE persistent tcgen05 kernel for the whole recurrence in each direction
-(csrc/lstm_seq_tcgen05.cu).  Generic path (any shape / fp32): library GEMM per step + the fused pointwise cell
+Fast path (bf16, H % 64 == 0, grid <= #SMs): hoisted input projection on the tcgen05 GEMM (csrc/gemm_tcgen05.cu) + ONE
+persistent tcgen05 kernel for the whole recurrence in each direction (csrc/lstm_seq_tcgen05.cu; weights resident in SMEM
+up to H = 1024, streamed through the ring above).  Generic path (any shape / fp32): library GEMM per step + the fused pointwise cell
 kernels (csrc/lstm_pointwise.cu).  Weight gradients are plain library GEMMs over all T at once
 (``[4H, T·B] x [T·B, D+H]``), fp32 output.  Math parity: /root/reference/src/models/recurrent/lstm.py:88-122.
 """
@@ -18,7 +18,12 @@ from .cuda_ext import ext
 _SYNC_WS = {}
 _SM_COUNT = {}
 FORCE_GENERIC = os.environ.get("LSTM_TS_FORCE_GENERIC", "0") == "1"
-SEQ_VARIANT = int(os.environ.get("LSTM_TS_SEQ_VARIANT", "0"))     # tuning knob: tiles_per_cta + 16*stages (0 = auto)
+# Tuning / experiment knob of the persistent kernels (0 = defaults), bit fields as decoded in csrc/lstm_seq_tcgen05.cu seq_common():
+#   [0:4) batch tiles per CTA (2 = one CTA alternates two tiles), [4:8) ring stages, bit 8 force streamed weights,
+#   [12:15) timing-only debug mode (1 skip loads, 2 skip MMAs, 3 in-order stream, 4 half-size loads, 5 no bookkeeping stores,
+#   6 no L2 prefetch, 7 cluster-scope acquire on the exchange barriers), [16:18) sync mode (0 per-k-block dataflow counters,
+#   1 one counter per batch tile = grid barrier, 2 per-CTA flags), bit 18 acquire polls, bit 19 no forward K-split.
+SEQ_VARIANT = int(os.environ.get("LSTM_TS_SEQ_VARIANT", "0"))
 USE_TC_GEMM = os.environ.get("LSTM_TS_TC_GEMM", "1") == "1"
 GEMM_VARIANT = int(os.environ.get("LSTM_TS_GEMM_VARIANT", "1"))   # 0: 128x128 tiles, 1: 128x256 tiles (faster on large shapes)
 STATS = {"fast_fwd": 0, "fast_bwd": 0, "generic_fwd": 0, "generic_bwd": 0, "tc_gemm": 0, "kernels": 0}
