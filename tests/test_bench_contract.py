@@ -39,3 +39,15 @@ def test_cuda_op_on_cpu_tensor_is_rejected_when_forced():
             F.lstm_cell_step(torch.zeros(2, 3), torch.zeros(2, 4), torch.zeros(2, 4), torch.zeros(16, 3), torch.zeros(16, 4), torch.zeros(16))
     finally:
         F.set_backend("auto")
+
+
+def test_clock_sampler_degrades_without_a_gpu():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cs = mod.ClockSampler(0)
+    cs.start()
+    cs.mark()
+    out = cs.stop()
+    assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons"}

@@ -149,3 +149,29 @@ def test_reference_state_dict_roundtrip():
     m2.load_reference_state_dict(sd)
     x = torch.randn(5, 4)
     assert torch.allclose(m1.features(x), m2.features(x))
+
+
+def test_fit_layers_returns_final_state_edge():
+    """fit_layers([B,T,D]) hands back the top layer's final state (a separate autograd edge, so the top layer never sees a
+    dense [T,B,H] gradient on the GPU path); value and gradients must equal the explicit seq[-1] route."""
+    import torch
+    from lstm_tensorspark_b200.models.recurrent.rnn import RNN
+    torch.manual_seed(0)
+    from lstm_tensorspark_b200.config import Config
+    rnn = RNN(Config(hidden_units="6,4", in_features=5, batch_size=3).net_settings(), init="scaled", learn_initial_state=False)
+    x = torch.randn(3, 7, 5)
+    out = rnn.fit_layers(x)
+    assert out.shape == (3, 4)
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    g1 = [p.grad.clone() for p in rnn.parameters() if p.grad is not None]
+    for p in rnn.parameters():
+        p.grad = None
+    rnn.reset_state(3)
+    seq = x.transpose(0, 1)
+    for layer in rnn.layers:
+        seq = layer.fit_sequence(seq)
+    assert torch.allclose(seq[-1], out, atol=1e-6)
+    (seq[-1] * w).sum().backward()
+    g2 = [p.grad.clone() for p in rnn.parameters() if p.grad is not None]
+    assert len(g1) == len(g2) and all(torch.allclose(a, b, atol=1e-6) for a, b in zip(g1, g2))
