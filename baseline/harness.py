@@ -67,8 +67,9 @@ class BaselineRunner:
         host_y = torch.as_tensor(ys).pin_memory()
         stage = [(torch.empty(B, T, D, dtype=torch.bfloat16, device=self.device),
                   torch.empty(B, dtype=torch.int64, device=self.device)) for _ in range(2)]
-        loss_host = torch.empty((), dtype=torch.float32, pin_memory=True)
-        it = {"i": 0, "slot": 0, "pending": None}
+        loss_host = torch.empty(2, dtype=torch.float32, pin_memory=True)
+        loss_evt = [torch.cuda.Event(), torch.cuda.Event()]
+        it = {"i": 0, "slot": 0, "pending": None, "k": 0, "last": float("nan")}
         copy_stream = torch.cuda.Stream(device=self.device)
 
         def issue():
@@ -97,7 +98,13 @@ class BaselineRunner:
             torch.cuda.current_stream(self.device).wait_event(ev)
             it["pending"] = issue()
             loss = self.train_step(sx, sy)
-            loss_host.copy_(loss.float())
+            k = it["k"]                              # same asynchronous, one-step-late loss read-back as the framework's arm
+            loss_host[k & 1].copy_(loss.float(), non_blocking=True)
+            loss_evt[k & 1].record()
+            if k > 0:
+                loss_evt[(k - 1) & 1].synchronize()
+                it["last"] = float(loss_host[(k - 1) & 1])
+            it["k"] = k + 1
             return loss_host
 
         h2d = B * T * D * 2 + B * 8

@@ -251,13 +251,24 @@ def main():
             return loss
 
         loader = Dm.PinnedHostLoader(xs, ys, B, device, dtype=torch.bfloat16, shuffle=False, seed=rank)
-        loss_host = torch.empty((), dtype=torch.float32, pin_memory=True)
+        loss_host = torch.empty(2, dtype=torch.float32, pin_memory=True)
+        loss_evt = [torch.cuda.Event(), torch.cuda.Event()]
+        e2e_state = {"i": 0, "last": float("nan")}
 
         def step_e2e():
-            x, y = loader.next()                       # pinned host -> device copy of this step's inputs
+            # every step: H2D of this step's batch (pinned, double-buffered on a copy stream) and a D2H read of its loss.
+            # The read-back is asynchronous (pinned buffer + event) and consumed one step later, so the host is already
+            # enqueueing step k+1 while step k runs - a blocking .item() per step would expose ~50 launch latencies.
+            i = e2e_state["i"]
+            x, y = loader.next()
             loss = eng.step(x, y)
             eng.maybe_average()
-            loss_host.copy_(loss.float(), non_blocking=False)    # device -> host read of the result
+            loss_host[i & 1].copy_(loss.float(), non_blocking=True)
+            loss_evt[i & 1].record()
+            if i > 0:
+                loss_evt[(i - 1) & 1].synchronize()
+                e2e_state["last"] = float(loss_host[(i - 1) & 1])     # the previous step's loss, on the host
+            e2e_state["i"] = i + 1
             return loss_host
 
         if args.cuda_graph:

@@ -686,6 +686,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
           for (int i = 0; i < 8; ++i) { dc[tile][i] = 0.f; dh[tile][i] = 0.f; }
         }
       }
+      U8 c_carry[kTiles];                       // c_t of the previous iteration = c_{t+1} of this one (one load per step, not two)
       for (int s = 0; s <= p.T && ok; ++s) {
         const int t = p.T - 1 - s;
 #pragma unroll
@@ -704,7 +705,9 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
             dhv = p.dh_seq ? ldg_nc16(p.dh_seq + ((size_t)t * B + row) * H + j0) : make_uint4(0u, 0u, 0u, 0u);
             const float* c0p = p.c_seq + ((size_t)t * B + row) * H + j0;
             const float* c1p = p.c_seq + ((size_t)(t + 1) * B + row) * H + j0;
-            cpv = ldg_nc32(c0p); cnv = ldg_nc32(c1p);
+            cpv = ldg_nc32(c0p);
+            cnv = (s == 0) ? ldg_nc32(c1p) : c_carry[tile];
+            c_carry[tile] = cpv;
             if (t >= 2) {                                                      // saved activations come from HBM: pull t-2 into L2 early
               prefetch_l2(ap - (size_t)2 * B * (4 * H));
               prefetch_l2(c0p - (size_t)2 * B * H);
