@@ -103,6 +103,17 @@ def fast_path_supported(B: int, H: int, dtype: torch.dtype, device) -> bool:
     return tiles_m * (H // 16) <= _sms(device) and tiles_m <= 16
 
 
+def _batch_chunk(B: int, H: int, dtype: torch.dtype, device) -> Optional[int]:
+    """Largest multiple of 128 rows whose CTAs fit the device, when the whole batch does not (else None)."""
+    if FORCE_GENERIC or dtype != torch.bfloat16 or H % 64 != 0 or fast_path_supported(B, H, dtype, device):
+        return None
+    tiles = _sms(device) // (H // 16)
+    if tiles < 1:
+        return None
+    chunk = min(tiles, 16) * 128
+    return chunk if chunk < B else None
+
+
 def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     if a.dtype == torch.float32:
         return a @ b
@@ -224,4 +235,15 @@ def lstm_layer_sequence(x_seq, h0, c0, w_x, w_h, bias):
             and (x_seq.shape[2] * x_seq.element_size()) % 16 == 0):
         x_seq = ext().transpose01(x_seq.transpose(0, 1))     # batch-major feed -> time-major, a row permutation at copy speed
         STATS["kernels"] += 1
+    T, B, _ = x_seq.shape
+    H = w_h.shape[1]
+    chunk = _batch_chunk(B, H, x_seq.dtype, x_seq.device)
+    if chunk is not None:
+        # more batch tiles than the persistent kernels can keep co-resident: the sequences are independent, so run the fast
+        # path per batch chunk (weight-gradient contributions accumulate across chunks) instead of the per-step generic path
+        outs = [_LSTMSeqFn.apply(x_seq[:, b0:b0 + chunk].contiguous(), h0[b0:b0 + chunk], c0[b0:b0 + chunk], w_x, w_h, bias)
+                for b0 in range(0, B, chunk)]
+        STATS["batch_chunks"] = STATS.get("batch_chunks", 0) + len(outs)
+        return (torch.cat([o[0] for o in outs], dim=1), torch.cat([o[1] for o in outs], dim=0),
+                torch.cat([o[2] for o in outs], dim=0))
     return _LSTMSeqFn.apply(x_seq.contiguous(), h0, c0, w_x, w_h, bias)

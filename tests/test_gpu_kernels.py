@@ -162,6 +162,14 @@ def test_persistent_lstm_final_state_gradients(dev, loss_on):
     _seq_case(dev, 4, 20, 32, 16, tol=3e-2, loss_on=loss_on)          # generic path
 
 
+def test_large_batch_runs_the_fast_path_in_chunks(dev):
+    """B = 400, H = 1024 needs 4 batch tiles x 64 CTAs > 148 SMs: two chunks of the persistent kernels, not the generic path."""
+    from lstm_tensorspark_b200.ops import cuda_lstm
+    n0 = cuda_lstm.STATS["fast_fwd"], cuda_lstm.STATS["generic_fwd"]
+    _seq_case(dev, 4, 400, 1024, 256, tol=3e-2, loss_on="all")
+    assert cuda_lstm.STATS["fast_fwd"] == n0[0] + 2 and cuda_lstm.STATS["generic_fwd"] == n0[1]
+
+
 @pytest.mark.parametrize("T,B,H,D", [(1, 10, 16, 4), (6, 33, 48, 20)])
 def test_generic_shape_lstm_sequence(dev, T, B, H, D):
     from lstm_tensorspark_b200.ops import cuda_lstm
