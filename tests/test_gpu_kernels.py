@@ -124,7 +124,8 @@ def _seq_case(dev, T, B, H, D, tol, loss_on="seq"):
         assert rel < 5 * tol, float(rel)
 
 
-@pytest.mark.parametrize("T,B,H,D", [(3, 128, 64, 64), (5, 100, 128, 72), (4, 256, 256, 128), (8, 256, 1024, 1024)])
+@pytest.mark.parametrize("T,B,H,D", [(1, 128, 64, 64), (1, 96, 128, 40), (2, 256, 256, 64), (3, 128, 64, 64), (5, 100, 128, 72),
+                                     (4, 256, 256, 128), (8, 256, 1024, 1024)])
 def test_persistent_tcgen05_lstm_sequence(dev, T, B, H, D):
     from lstm_tensorspark_b200.ops import cuda_lstm
     n0 = cuda_lstm.STATS["fast_fwd"], cuda_lstm.STATS["fast_bwd"]
@@ -176,6 +177,33 @@ def test_generic_shape_lstm_sequence(dev, T, B, H, D):
     n0 = cuda_lstm.STATS["generic_fwd"]
     _seq_case(dev, T, B, H, D, tol=3e-2)
     assert cuda_lstm.STATS["generic_fwd"] == n0 + 1
+
+
+def test_single_step_cell_uses_the_persistent_kernels(dev):
+    """The reference applies every layer for exactly ONE time step (fit_next on [B,D]); on the GPU that is the T = 1 case of
+    the same persistent kernels."""
+    from lstm_tensorspark_b200.ops import cuda_lstm, functional as F
+    ref = _ref()
+    torch.manual_seed(3)
+    B, D, H = 128, 64, 128
+    x = torch.randn(B, D, device=dev) * 0.5
+    h = torch.randn(B, H, device=dev) * 0.1
+    c = torch.randn(B, H, device=dev) * 0.1
+    w_x = (torch.randn(4 * H, D, device=dev) / D ** 0.5).requires_grad_(True)
+    w_h = (torch.randn(4 * H, H, device=dev) / H ** 0.5).requires_grad_(True)
+    b = (torch.randn(4 * H, device=dev) * 0.1).requires_grad_(True)
+    n0 = cuda_lstm.STATS["fast_fwd"]
+    F.set_backend("cuda_ext")
+    try:
+        h1, c1 = F.lstm_cell_step(x.bfloat16(), h, c, w_x, w_h, b)
+    finally:
+        F.set_backend("auto")
+    assert cuda_lstm.STATS["fast_fwd"] == n0 + 1
+    hr, cr = ref.lstm_cell_step(x.bfloat16().float(), h, c, w_x.detach().bfloat16().float(), w_h.detach().bfloat16().float(), b.detach())
+    assert (h1.float() - hr).abs().max() < 3e-2 and (c1.float() - cr).abs().max() < 3e-2
+    (h1.float().sum() + c1.float().sum()).backward()
+    assert w_x.grad is not None and w_h.grad is not None and torch.isfinite(w_h.grad).all()
+    cuda_lstm.check_kernel_errors(dev)
 
 
 def test_engine_step_trains_and_uses_kernels(dev):
