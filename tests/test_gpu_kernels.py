@@ -125,7 +125,7 @@ def _seq_case(dev, T, B, H, D, tol, loss_on="seq"):
 
 
 @pytest.mark.parametrize("T,B,H,D", [(1, 128, 64, 64), (1, 96, 128, 40), (2, 256, 256, 64), (3, 128, 64, 64), (5, 100, 128, 72),
-                                     (4, 256, 256, 128), (8, 256, 1024, 1024)])
+                                     (4, 256, 256, 128), (8, 256, 1024, 1024), (3, 64, 2048, 256)])    # last: streamed-weights variant
 def test_persistent_tcgen05_lstm_sequence(dev, T, B, H, D):
     from lstm_tensorspark_b200.ops import cuda_lstm
     n0 = cuda_lstm.STATS["fast_fwd"], cuda_lstm.STATS["fast_bwd"]
