@@ -21,7 +21,7 @@ class Config:
     # ---- reference flags (rnn.py:310-334) -------------------------------------------------------
     master: str = "local"               # accepted for CLI compatibility, unused (no Spark)
     spark_exec_memory: str = "4g"       # accepted for CLI compatibility, unused
-    partitions: int = 4                 # number of data shards == ranks == GPUs
+    partitions: int = 4                 # number of data shards / replicas (one rank per GPU while GPUs last)
     epochs: int = 1
     hidden_units: str = "128,256"
     batch_size: int = 10                # 0 => whole shard in one batch (reference intent, Q3)
@@ -61,6 +61,8 @@ class Config:
     trace: str = ""                     # path for a torch.profiler chrome trace
     nvtx: bool = False
     json_log: str = ""                  # machine readable metrics file
+    max_workers: int = 0                # ranks that run concurrently (Spark's local[N]); 0 = min(partitions, visible GPUs) on
+                                        # CUDA, = partitions on the CPU.  partitions > workers: a rank trains its partitions in turn
     fault_inject: str = ""              # "rank:step" => that rank exits abnormally at that step (test hook)
     timeout_s: float = 600.0
     quiet: bool = False

@@ -240,6 +240,10 @@ class PinnedHostLoader:
         self.bytes_per_batch = self.dev[0][0].numel() * self.dev[0][0].element_size() + self.batch_size * 8
 
     def _reshuffle(self):
+        # the async H2D copy of the last batch of the previous pass may not have run yet (the host is ahead of the GPU):
+        # it must not read pinned memory that is being re-permuted underneath it
+        if self._copy_stream is not None:
+            self._copy_stream.synchronize()
         perm = torch.randperm(self.n, generator=self.gen)
         xs, ys = self.x_host[perm], self.y_host[perm]
         self.x_host.copy_(xs)

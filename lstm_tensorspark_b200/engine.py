@@ -96,6 +96,12 @@ class TrainEngine:
         a device-resident step counter, so replays are exact."""
         assert self.device.type == "cuda"
         sx, sy = x.clone(), y.clone()
+        # warm-up / capture run real updates: snapshot the training state and put it back, so capturing is not
+        # `warmup` uncounted optimizer steps on one batch and the host / device Adam step counters stay equal
+        opt = self.optimizer
+        snap = {"data": self.flat.data.clone(), "step_count": opt.step_count,
+                "m": None if opt.m is None else opt.m.clone(), "v": None if opt.v is None else opt.v.clone(),
+                "step_dev": None if opt.step_dev is None else opt.step_dev.clone()}
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -105,6 +111,14 @@ class TrainEngine:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             sloss = self._step_eager(sx, sy)
+        with torch.no_grad():
+            self.flat.data.copy_(snap["data"])
+            self.flat.refresh_shadow()
+            if snap["m"] is not None:
+                opt.m.copy_(snap["m"]); opt.v.copy_(snap["v"])
+            if snap["step_dev"] is not None:
+                opt.step_dev.copy_(snap["step_dev"])
+            opt.step_count = snap["step_count"]
         self._graph, self._static = g, (sx, sy, sloss)
         return g
 

@@ -94,20 +94,41 @@ def _sms(device) -> int:
     return _SM_COUNT[key]
 
 
+_CORES = {}
+
+
+def _coresident_ctas(device) -> int:
+    """CTAs of the persistent kernels that can be co-resident: the backward kernel runs in clusters of 4 (measured on
+    B200: 33 clusters = 132 CTAs of 148 SMs), the forward K-split in clusters of 2."""
+    key = device.index
+    if key not in _CORES:
+        n = _sms(device)
+        try:
+            with torch.cuda.device(device):
+                c4 = int(ext().lstm_seq_cluster_probe(4))
+            if c4 > 0:
+                n = min(n, 4 * c4)
+        except Exception:                                   # noqa: BLE001
+            pass
+        _CORES[key] = n
+    return _CORES[key]
+
+
 def fast_path_supported(B: int, H: int, dtype: torch.dtype, device) -> bool:
     if FORCE_GENERIC or dtype != torch.bfloat16 or H % 64 != 0:
         return False
     tiles_m = (B + 127) // 128
-    # one CTA per (batch tile, 64 gate columns); all of them must be co-resident (grid barrier).  The weight slice stays in
-    # shared memory when it fits (H <= 1024), larger H streams it through the ring (csrc/lstm_seq_tcgen05.cu, kStream)
-    return tiles_m * (H // 16) <= _sms(device) and tiles_m <= 16
+    # one CTA per (batch tile, 64 gate columns); all of them must be co-resident (dataflow sync between CTAs), in clusters
+    # of 4 for the backward pass.  The weight slice stays in shared memory when it fits (H <= 1024), larger H streams it
+    # through the ring (csrc/lstm_seq_tcgen05.cu, kStream)
+    return tiles_m * (H // 16) <= _coresident_ctas(device) and tiles_m <= 16
 
 
 def _batch_chunk(B: int, H: int, dtype: torch.dtype, device) -> Optional[int]:
     """Largest multiple of 128 rows whose CTAs fit the device, when the whole batch does not (else None)."""
     if FORCE_GENERIC or dtype != torch.bfloat16 or H % 64 != 0 or fast_path_supported(B, H, dtype, device):
         return None
-    tiles = _sms(device) // (H // 16)
+    tiles = _coresident_ctas(device) // (H // 16)
     if tiles < 1:
         return None
     chunk = min(tiles, 16) * 128

@@ -62,6 +62,14 @@ class Communicator:
         """Checkpointable optimizer state (complete on every rank)."""
         return optimizer.state_dict()
 
+    def load_optimizer_state(self, optimizer, sd: dict):
+        """Inverse of ``optimizer_state`` (the fused back end keeps only its own slice of Adam's m / v)."""
+        optimizer.load_state_dict(sd)
+
+    def allreduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
+        """Plain elementwise sum over ranks of a (CPU or device) tensor - job finalisation only, never on the step path."""
+        return t
+
     def close(self):
         pass
 
@@ -116,6 +124,12 @@ class TorchDistComm(Communicator):
     def broadcast_params_(self, flat: FlatParams, src: int = 0):
         dist.broadcast(flat.data, src=src)
         flat.refresh_shadow()
+
+    def allreduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
+        buf = t.to(self.device) if self.name == "nccl" else t.cpu()
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        t.copy_(buf.to(t.device))
+        return t
 
     def close(self):
         if dist.is_initialized():

@@ -83,6 +83,7 @@ class FusedComm(TorchDistComm):
         self.use_multicast = os.environ.get("LSTM_TS_AR_MULTICAST", "auto")
         self.blocks_override = 0          # tuning knob (bench/allreduce_sweep.py)
         self.launches = 0
+        self._sliced_state = False        # True once a two-shot fused Adam step has run (m / v maintained per owned slice)
 
     # ------------------------------------------------------------------------------------------------
     def adopt(self, flat: FlatParams):
@@ -146,23 +147,40 @@ class FusedComm(TorchDistComm):
         optimizer.step_count += 1
         n = flat.padded_numel
         if optimizer.kind == "adam":
+            two_shot = (4 * n >= TWO_SHOT_BYTES) if force is None else (force == "two_shot")
+            self._sliced_state = self._sliced_state or two_shot
             self._launch(MODE_ADAM, self.off_grad, n, optimizer.lr, optimizer.beta1, optimizer.beta2,
                          optimizer.eps, optimizer.weight_decay, optimizer.m, optimizer.v, force=force,
                          step_dev=optimizer.step_dev)
         else:
             self._launch(MODE_SGD, self.off_grad, n, optimizer.lr, wd=optimizer.weight_decay, force=force)
 
+    def _owned_slice(self, n: int):
+        """Element range of the flat buffer whose Adam slots THIS rank maintains in the two-shot gradient step
+        (same split as csrc/fused_allreduce.cu: ceil(n4 / world) float4 per rank)."""
+        n4 = n // 4
+        per = (n4 + self.world_size - 1) // self.world_size
+        lo = min(per * self.rank, n4)
+        hi = min(lo + per, n4)
+        return 4 * lo, 4 * hi
+
     def optimizer_state(self, optimizer) -> dict:
-        """Two-shot gradient sync keeps Adam's (m, v) for 1/N of the elements on each rank (the slice it reduces and
-        updates); the other entries stay zero, so a SUM across ranks reassembles the full state for a checkpoint."""
+        """The two-shot fused gradient step keeps Adam's (m, v) for 1/N of the elements on each rank (the slice it
+        reduces and updates).  A checkpoint holds the FULL state: every rank contributes exactly its owned slice
+        (everything else masked to zero, whatever it holds) and a sum reassembles it.  Any other mode (parameter
+        averaging: every rank runs its own full optimizer; one-shot: full state everywhere) returns the local state."""
         sd = optimizer.state_dict()
-        n = self.flat.padded_numel
-        if optimizer.kind == "adam" and self.world_size > 1 and 4 * n >= TWO_SHOT_BYTES and optimizer.step_count > 0:
+        if self._sliced_state and optimizer.kind == "adam" and self.world_size > 1:
+            lo, hi = self._owned_slice(self.flat.padded_numel)
             for k in ("m", "v"):
-                full = getattr(optimizer, k).detach().clone()
+                full = torch.zeros_like(getattr(optimizer, k))
+                full[lo:hi] = getattr(optimizer, k)[lo:hi]
                 dist.all_reduce(full, op=dist.ReduceOp.SUM)
                 sd[k] = full.cpu()
         return sd
+
+    def load_optimizer_state(self, optimizer, sd: dict):
+        optimizer.load_state_dict(sd)          # full m / v everywhere; the two-shot step only ever reads the owned slice
 
     def check_errors(self):
         if int(self.err.item()) != 0:

@@ -46,7 +46,8 @@ def resolve_device(cfg: Config, rank: int) -> torch.device:
         raise RuntimeError("--device cuda requested but no GPU is visible")
     local = int(os.environ.get("LOCAL_RANK", rank))
     if local >= n:
-        raise RuntimeError(f"--partitions needs {local + 1} GPUs, only {n} visible (Q14: one rank per GPU)")
+        raise RuntimeError(f"rank {rank} needs GPU {local}, only {n} visible (run_job maps partitions beyond the GPU count "
+                           "round-robin onto the visible ones; a torchrun world larger than the box is an error)")
     torch.cuda.set_device(local)
     return torch.device("cuda", local)
 
@@ -82,7 +83,7 @@ def _check_device_errors(device: torch.device, comm) -> None:
 
 def train_rnn(partition, cfg: Config, rank: int = 0, world_size: int = 1, comm: Optional[Communicator] = None,
               train_optimizer: Optional[Callable] = None, standalone: bool = False,
-              run_stamp: Optional[str] = None) -> Optional[ReplicaResult]:
+              run_stamp: Optional[str] = None, defer_average: bool = False) -> Optional[ReplicaResult]:
     """Train one replica on one shard.  ``partition`` = ``(key, rows)`` (distributed) or a list of rows
     (standalone) or ``(key, (x ndarray, y ndarray))`` for pre-parsed / synthetic data."""
     comm = comm or Communicator(0, 1)
@@ -125,22 +126,33 @@ def train_rnn(partition, cfg: Config, rank: int = 0, world_size: int = 1, comm: 
     sink = M.SummarySink(os.path.join(model_save_dir, "train"))
     jlog = M.JsonLog(cfg.json_log)
 
+    loader = D.DeviceShard(train_x, train_y, batch_size, device, dtype=torch.float32, shuffle=True,
+                           seed=cfg.seed + 17 * (rank + 1))
     start_step = 0
     if cfg.resume or cfg.use_pretrained_model:
         src = cfg.resume or ckpt.find_latest_run(cfg.checkpoint_path, None if standalone else str(partition_key))
         if src and os.path.isdir(src):
+            if not standalone and ckpt.latest_checkpoint(src) is None and os.path.isdir(os.path.join(src, str(partition_key))):
+                src = os.path.join(src, str(partition_key))        # --resume <run dir>: every rank picks its own partition
             src = ckpt.latest_checkpoint(src)
         if src:
             variables, meta, opt_state = ckpt.load(src)
             model.load_reference_state_dict(variables, strict=False)
+            eng.flat.refresh_shadow()
             if opt_state is not None:
-                optimizer.load_state_dict(opt_state["optimizer"])
+                comm.load_optimizer_state(optimizer, opt_state["optimizer"])
+                if opt_state.get("loader") is not None:
+                    loader.load_state_dict(opt_state["loader"])      # continue the data order, do not replay it
             start_step = int(meta.get("global_step", -1)) + 1
             if not cfg.quiet:
                 print(f"{tag} - restored {src} (resuming at step {start_step})")
+        # every rank must resume at the same step (per-step collectives would otherwise mismatch): fail loudly if not
+        if world_size > 1:
+            hi_s, lo_s = comm.max_scalar(float(start_step)), -comm.max_scalar(-float(start_step))
+            if hi_s != lo_s:
+                raise RuntimeError(f"{tag} - ranks disagree on the resume step (min {int(lo_s)}, max {int(hi_s)}): "
+                                   "a checkpoint is missing or stale on some rank")
 
-    loader = D.DeviceShard(train_x, train_y, batch_size, device, dtype=torch.float32, shuffle=True,
-                           seed=cfg.seed + 17 * (rank + 1))
     max_steps = compute_max_steps(cfg, batch_size, loader.per_epoch)
 
     use_bar = (trange is not None) and (rank == 0) and not cfg.quiet
@@ -159,6 +171,7 @@ def train_rnn(partition, cfg: Config, rank: int = 0, world_size: int = 1, comm: 
         fr, fs = cfg.fault_inject.split(":")
         fault = (int(fr), int(fs))
 
+    bar_loss = M.LaggedScalar(device)
     timer = M.DeviceTimer(device)
     start = time.time()
     timer.start()
@@ -181,8 +194,10 @@ def train_rnn(partition, cfg: Config, rank: int = 0, world_size: int = 1, comm: 
             eng.maybe_average()
 
         is_eval = (step % cfg.evaluate_every == 0) or (step + 1) == max_steps
-        if use_bar or is_eval:
+        if is_eval:
             t_loss = float(loss.detach().float().item())
+        elif use_bar:
+            t_loss = bar_loss.push(loss)         # CUDA: the previous step's loss, read back asynchronously (no host sync)
         if use_bar:
             total_steps.set_description("Loss: {:.4f} - t_acc {:.3f}".format(t_loss, t_acc))
 
@@ -206,7 +221,8 @@ def train_rnn(partition, cfg: Config, rank: int = 0, world_size: int = 1, comm: 
 
     # ---- the cross-replica average (src/rnn.py:393-407) ------------------------------------------------
     with M.nvtx_range("final_param_avg", cfg.nvtx):
-        eng.maybe_average(force=True)
+        if not defer_average:                   # oversubscribed ranks average all their replicas at once (_rank_main)
+            eng.maybe_average(force=True)
     device_ms = timer.stop_ms()
     end_time = time.time() - start
     n_steps = max(1, max_steps - start_step)
@@ -222,6 +238,10 @@ def train_rnn(partition, cfg: Config, rank: int = 0, world_size: int = 1, comm: 
     result = ReplicaResult(partition_key=partition_key, rank=rank, records=records,
                            variables=model.reference_state_dict(), loss=t_loss, acc=t_acc, steps=n_steps,
                            seconds=end_time, device_ms=device_ms, samples=samples, model_save_dir=model_save_dir)
+    if defer_average:
+        lo, hi = eng.flat.segment(cfg.average_scope)
+        result["flat_scope"] = eng.flat.data[lo:hi].detach().float().cpu().clone()
+        result["batch_size"] = batch_size
     jlog.write(event="done", rank=rank, seconds=end_time, device_ms=device_ms, samples_per_s=samples / max(end_time, 1e-9))
     sink.close()
     jlog.close()
@@ -236,8 +256,12 @@ def _rank_main(rank: int, world_size: int, cfg: Config, shards, standalone: bool
     comm = make_communicator(cfg.comm, rank, world_size, device, cfg.timeout_s)
     try:
         stamp = comm.broadcast_object(str(time.time()), src=0)
-        shard = shards[rank] if shards is not None else None
-        res = train_rnn(shard, cfg, rank, world_size, comm, standalone=standalone, run_stamp=stamp)
+        mine = list(shards[rank::world_size]) if shards is not None else [None]
+        if len(shards or []) <= world_size:
+            shard = shards[rank] if shards is not None else None
+            res = train_rnn(shard, cfg, rank, world_size, comm, standalone=standalone, run_stamp=stamp)
+        else:
+            res = _train_oversubscribed(mine, len(shards), cfg, rank, world_size, comm, stamp)
         comm.barrier()
         if res is not None and rank != 0:
             # only rank 0's records are needed by the driver (all replicas hold the same average)
@@ -245,6 +269,52 @@ def _rank_main(rank: int, world_size: int, cfg: Config, shards, standalone: bool
         return res
     finally:
         comm.close()
+
+
+def _train_oversubscribed(mine, n_partitions: int, cfg: Config, rank: int, world_size: int, comm, stamp: str):
+    """More partitions than workers (the reference runs ``--partitions`` tasks on ``local[workers]`` executor threads,
+    /root/reference/src/rnn.py:355-358: each worker takes its tasks in turn).  Every partition is still its own replica
+    with its own checkpoint directory; a rank trains its partitions one after the other and the one-shot average at the
+    end of the job (src/rnn.py:393-407) runs over ALL partitions: local sum -> cross-rank sum -> / partitions."""
+    results = []
+    for shard in mine:
+        results.append(train_rnn(shard, cfg, rank, 1, None, standalone=False, run_stamp=stamp, defer_average=True))
+    results = [r for r in results if r is not None]
+    if not results:
+        return None
+    total = torch.zeros_like(results[0]["flat_scope"])
+    for r in results:
+        total += r["flat_scope"]
+    count = torch.tensor([float(len(results))], dtype=torch.float64)
+    if world_size > 1:
+        comm.allreduce_sum_(total)
+        comm.allreduce_sum_(count)
+    mean = total / float(count.item())
+    # rebuild the exported records from the averaged flat segment (everything outside the scope: this rank's first replica)
+    r0 = results[0]
+    model = SequenceClassifier(cfg, batch_size=r0["batch_size"], device="cpu")
+    model.load_reference_state_dict(r0["variables"], strict=False)
+    flat = model.build_flat()
+    lo, hi = flat.segment(cfg.average_scope)
+    with torch.no_grad():
+        flat.data[lo:hi].copy_(mean)
+    records = [(k, [[t.detach().float().cpu().clone() for t in layer] if isinstance(layer, list)
+                    else layer.detach().float().cpu().clone() for layer in v]) for k, v in model.rnn.map_data_by_key()]
+    out = ReplicaResult({k: v for k, v in r0.items() if k not in ("flat_scope",)})
+    out.update(records=records, variables=model.reference_state_dict(), partitions_trained=[r["partition_key"] for r in results],
+               seconds=sum(r["seconds"] for r in results), samples=sum(r["samples"] for r in results))
+    return out
+
+
+def resolve_workers(cfg: Config, standalone: bool) -> int:
+    """Concurrent ranks for ``--partitions`` replicas: one per GPU while GPUs last (Q14), round-robin beyond that."""
+    if standalone:
+        return 1
+    cap = cfg.max_workers
+    if cap <= 0:
+        on_gpu = cfg.device == "cuda" or (cfg.device == "auto" and torch.cuda.is_available())
+        cap = max(1, torch.cuda.device_count()) if on_gpu else cfg.partitions
+    return max(1, min(cfg.partitions, cap))
 
 
 def load_shards(cfg: Config, world_size: int, standalone: bool):
@@ -263,12 +333,19 @@ def load_shards(cfg: Config, world_size: int, standalone: bool):
 def run_job(cfg: Config, standalone: bool = False) -> Dict:
     """``main`` of both entry points: shard -> N replicas -> average -> output."""
     from .parallel.launch import launch, in_torchrun
-    world_size = 1 if standalone else cfg.partitions
+    world_size = resolve_workers(cfg, standalone)
     if in_torchrun():
         world_size = int(os.environ["WORLD_SIZE"])
+    n_shards = 1 if standalone else max(cfg.partitions, world_size)
+    if n_shards > world_size:
+        if cfg.sync_mode == "grad_allreduce" or (cfg.sync_mode == "param_avg" and cfg.sync_every):
+            raise ValueError(f"--partitions {cfg.partitions} > {world_size} workers needs the one-shot parameter average "
+                             "(--sync_mode param_avg --sync_every 0): replicas that take turns cannot sync every step")
+        sys.stderr.write(f"RNN-LSTM - warning: {n_shards} partitions on {world_size} workers: each worker trains its "
+                         "partitions in turn (round-robin), the final average runs over all partitions\n")
     if not cfg.quiet:
         print("Total workers: ", f"[{world_size}]")
-    shards = load_shards(cfg, world_size, standalone)
+    shards = load_shards(cfg, n_shards, standalone)
     start = time.time()
     results = launch(_rank_main, world_size, args=(cfg, shards, standalone))
     total = time.time() - start
@@ -279,4 +356,4 @@ def run_job(cfg: Config, standalone: bool = False) -> Dict:
                                   "hidden_units": cfg.hidden_units, "seconds": total})
     if not cfg.quiet:
         print("RNN-LSTM - Total Processing Time {}s".format(total))
-    return {"results": results, "seconds": total, "world_size": world_size}
+    return {"results": results, "seconds": total, "world_size": world_size, "partitions": n_shards}

@@ -98,6 +98,33 @@ class DeviceTimer:
         return (time.perf_counter() - self.t0) * 1e3
 
 
+class LaggedScalar:
+    """Per-step scalar for the progress bar without a per-step host sync: on CUDA the value is copied into a pinned
+    buffer asynchronously and the PREVIOUS step's value is returned (its copy has long finished); on the CPU it is exact.
+    (The reference's ``sess.run([train_op, loss])`` blocks on the loss every step, /root/reference/src/rnn.py:264-271.)"""
+
+    def __init__(self, device):
+        self.cuda = torch.device(device).type == "cuda"
+        self.last = float("nan")
+        if self.cuda:
+            self.host = torch.empty(2, dtype=torch.float32, pin_memory=True)
+            self.evt = [torch.cuda.Event(), torch.cuda.Event()]
+            self.k = 0
+
+    def push(self, value: torch.Tensor) -> float:
+        if not self.cuda:
+            self.last = float(value.detach().float().item())
+            return self.last
+        k = self.k
+        self.host[k & 1].copy_(value.detach().float(), non_blocking=True)
+        self.evt[k & 1].record()
+        if k > 0:
+            self.evt[(k - 1) & 1].synchronize()
+            self.last = float(self.host[(k - 1) & 1])
+        self.k = k + 1
+        return self.last
+
+
 @contextlib.contextmanager
 def nvtx_range(name: str, enabled: bool = True):
     on = enabled and torch.cuda.is_available()

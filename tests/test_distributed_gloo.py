@@ -94,3 +94,28 @@ def test_rank_failure_is_an_error_not_a_hang(tmp_path, iris_path):
     with pytest.raises(RankFailure) as ei:
         run_job(cfg, standalone=False)
     assert ei.value.exit_codes[1] == 17
+
+
+def test_more_partitions_than_workers_round_robin(tmp_path, iris_path, capfd):
+    """--partitions 4 on 2 workers (Spark local[2] with 4 tasks, /root/reference/src/rnn.py:355-358): every partition gets
+    its own replica + checkpoint dir, ranks take their partitions in turn, the final average runs over all 4."""
+    cfg = _cfg(tmp_path, iris_path, partitions=4, max_workers=2)
+    out = run_job(cfg, standalone=False)
+    assert out["world_size"] == 2 and out["partitions"] == 4
+    assert "4 partitions on 2 workers" in capfd.readouterr().err
+    runs = os.listdir(cfg.checkpoint_path)
+    assert len(runs) == 1
+    assert sorted(os.listdir(os.path.join(cfg.checkpoint_path, runs[0]))) == ["0", "1", "2", "3"]
+    avg = torch.load(os.path.join(cfg.output_path, "averaged_model.pt"), weights_only=False)
+    # the exported average equals the mean of the four replicas' final checkpoints
+    from lstm_tensorspark_b200.utils import checkpoint as ckpt
+    finals = [ckpt.load(ckpt.latest_checkpoint(os.path.join(cfg.checkpoint_path, runs[0], str(k))))[0] for k in range(4)]
+    mean_wf_h = torch.stack([f["LSTMLayer0/weights_forget_h"] for f in finals]).mean(0)
+    assert torch.allclose(avg["records"]["wf"][0][0], mean_wf_h, atol=1e-6)
+    assert out["results"][0]["partitions_trained"] == [0, 2] and out["results"][1]["partitions_trained"] == [1, 3]
+
+
+def test_oversubscription_needs_the_one_shot_average(tmp_path, iris_path):
+    cfg = _cfg(tmp_path, iris_path, partitions=4, max_workers=2, sync_mode="grad_allreduce")
+    with pytest.raises(ValueError):
+        run_job(cfg, standalone=False)

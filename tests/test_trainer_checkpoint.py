@@ -88,3 +88,29 @@ def test_saver_retention_and_index(tmp_path):
     assert sorted(f for f in os.listdir(tmp_path) if f.endswith(".index")) == ["spark_lstm-10.index", "spark_lstm-20.index"]
     idx = open(tmp_path / "checkpoint").read()
     assert 'model_checkpoint_path: "spark_lstm-20"' in idx and idx.count("all_model_checkpoint_paths") == 2
+
+
+def _final_state(cfg):
+    d = ckpt.find_latest_run(cfg.checkpoint_path, None)
+    return ckpt.load(ckpt.latest_checkpoint(d))
+
+
+def test_resume_is_equivalent_to_an_uninterrupted_run(tmp_path, iris_path):
+    """8 steps straight == 4 steps + resume + 4 steps, bit for bit: weights, Adam slots, step counter AND the position in
+    the data order (the loader state is restored, not replayed from the first permutation)."""
+    common = dict(evaluate_every=1, learning_rate=1e-2)
+    a = _cfg(tmp_path / "a", iris_path, max_steps=8, **common)
+    run_job(a, standalone=True)
+    va, ma, oa = _final_state(a)
+    b1 = _cfg(tmp_path / "b", iris_path, max_steps=4, **common)
+    run_job(b1, standalone=True)
+    b2 = _cfg(tmp_path / "b", iris_path, max_steps=8, use_pretrained_model=True, **common)
+    out = run_job(b2, standalone=True)
+    assert out["results"][0]["steps"] == 4
+    vb, mb, ob = _final_state(b2)
+    assert ma["global_step"] == mb["global_step"] == 7
+    for k in va:
+        assert torch.equal(va[k], vb[k]), k
+    assert oa["optimizer"]["step"] == ob["optimizer"]["step"] == 8
+    assert torch.equal(oa["optimizer"]["m"], ob["optimizer"]["m"]) and torch.equal(oa["optimizer"]["v"], ob["optimizer"]["v"])
+    assert oa["loader"]["i"] == ob["loader"]["i"] and torch.equal(oa["loader"]["perm"], ob["loader"]["perm"])
