@@ -84,34 +84,69 @@ def check_simple():
     _emit("flat_adam", p_err=float((p - p2).abs().max()), shadow_err=float((sh.float() - p).abs().max()))
 
 
-def check_gemm():
+def check_gemm2():
+    """General tcgen05 GEMM: every operand-major combination, 1- and 2-CTA tiles, accumulate, ragged shapes, then timing
+    of the training-step shapes against cuBLAS."""
     import torch
     from lstm_tensorspark_b200.ops.cuda_ext import ext
     E = ext()
     dev = torch.device("cuda")
     torch.manual_seed(0)
-    shapes = [(128, 128, 64), (128, 128, 256), (256, 256, 512), (384, 1024, 1024), (1000, 520, 264), (32768, 4096, 1024)]
-    for variant in (0, 1):
-        for (M, N, K) in shapes:
-            A = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
-            Bm = (torch.randn(N, K, device=dev) * 0.5).bfloat16()
-            bias = torch.randn(N, device=dev)
-            try:
-                Cc = E.gemm_bf16_tn(A, Bm, bias, True, variant)
-                torch.cuda.synchronize()
-                if M * N <= 4096 * 4096:
-                    R = A.float() @ Bm.float().t() + bias
-                    err = float((Cc - R).abs().max()); rel = err / float(R.abs().max())
-                else:
-                    R = (A[:256].float() @ Bm.float().t() + bias)
-                    err = float((Cc[:256] - R).abs().max()); rel = err / float(R.abs().max())
-                ms = _time_ms(lambda: E.gemm_bf16_tn(A, Bm, None, False, variant))
-                ms_cublas = _time_ms(lambda: A @ Bm.t())
-                _emit("gemm", variant=variant, M=M, N=N, K=K, max_err=err, rel_err=rel, ms=ms, tflops=2.0 * M * N * K / ms / 1e9,
-                      cublas_ms=ms_cublas, cublas_tflops=2.0 * M * N * K / ms_cublas / 1e9)
-            except Exception as e:                # noqa: BLE001
-                _emit("gemm", variant=variant, M=M, N=N, K=K, error=repr(e)[:400])
-                raise
+    small = [(128, 128, 64), (256, 256, 128), (512, 512, 256), (1000, 520, 264), (384, 1024, 1024)]
+    for ctas, bn in ((1, 128), (1, 256), (2, 128), (2, 256)):
+        for a_mn in (False, True):
+            for b_mn in (False, True):
+                worst = 0.0
+                for (M, N, K) in small:
+                    A = (torch.randn(K, M, device=dev) * 0.5).bfloat16() if a_mn else (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+                    Bm = (torch.randn(K, N, device=dev) * 0.5).bfloat16() if b_mn else (torch.randn(N, K, device=dev) * 0.5).bfloat16()
+                    R = (A.float().t() if a_mn else A.float()) @ (Bm.float() if b_mn else Bm.float().t())
+                    try:
+                        C16 = E.gemm2(A, Bm, a_mn=a_mn, b_mn=b_mn, ctas=ctas, bn=bn)
+                        C32 = E.gemm2(A, Bm, a_mn=a_mn, b_mn=b_mn, out_fp32=True, ctas=ctas, bn=bn)
+                        acc = torch.ones(M, N, device=dev)
+                        E.gemm2(A, Bm, out=acc, a_mn=a_mn, b_mn=b_mn, accumulate=True, ctas=ctas, bn=bn)
+                        torch.cuda.synchronize()
+                        scale = float(R.abs().max())
+                        e16 = float((C16.float() - R).abs().max()) / scale
+                        e32 = float((C32 - R).abs().max()) / scale
+                        eac = float((acc - 1.0 - R).abs().max()) / scale
+                        worst = max(worst, e16 / 8.0, e32, eac)       # bf16 output rounding allowed 8x
+                        if max(e32, eac) > 2e-3 or e16 > 1.6e-2:
+                            _emit("gemm2_MISMATCH", ctas=ctas, bn=bn, a_mn=a_mn, b_mn=b_mn, M=M, N=N, K=K, e16=e16, e32=e32, eacc=eac)
+                    except Exception as e:            # noqa: BLE001
+                        _emit("gemm2_ERROR", ctas=ctas, bn=bn, a_mn=a_mn, b_mn=b_mn, M=M, N=N, K=K, error=repr(e)[:300])
+                        raise
+                _emit("gemm2", ctas=ctas, bn=bn, a_mn=a_mn, b_mn=b_mn, worst_rel_err=worst)
+    # strided operands (views of wider buffers)
+    big = (torch.randn(512, 1536, device=dev) * 0.5).bfloat16()
+    A, Bm = big[:, :512], big[:256, 512:1024]
+    C = E.gemm2(A, Bm, out_fp32=True)
+    R = A.float() @ Bm.float().t()
+    _emit("gemm2_strided", rel_err=float((C - R).abs().max() / R.abs().max()))
+    # timing: x-projection (TN), dX (NN), dW (NT = both MN-major), head-sized
+    TB, H4, D = 32768, 4096, 1024
+    X = (torch.randn(TB, D, device=dev) * 0.5).bfloat16()
+    W = (torch.randn(H4, D, device=dev) * 0.05).bfloat16()
+    dG = (torch.randn(TB, H4, device=dev) * 0.5).bfloat16()
+    gw = torch.zeros(H4, D, device=dev)
+    for ctas, bn in ((1, 256), (2, 256), (2, 128)):
+        ms = _time_ms(lambda: E.gemm2(X, W, ctas=ctas, bn=bn))
+        _emit("gemm2_time", what="gx = X Wx^T", ctas=ctas, bn=bn, ms=ms, tflops=2.0 * TB * H4 * D / ms / 1e9)
+        ms = _time_ms(lambda: E.gemm2(dG, W, b_mn=True, ctas=ctas, bn=bn))
+        _emit("gemm2_time", what="dX = dG Wx", ctas=ctas, bn=bn, ms=ms, tflops=2.0 * TB * H4 * D / ms / 1e9)
+        ms = _time_ms(lambda: E.gemm2(dG, X, out=gw, a_mn=True, b_mn=True, accumulate=True, ctas=ctas, bn=bn))
+        _emit("gemm2_time", what="dW += dG^T X", ctas=ctas, bn=bn, ms=ms, tflops=2.0 * TB * H4 * D / ms / 1e9)
+    ms = _time_ms(lambda: X @ W.t())
+    _emit("gemm2_time", what="cuBLAS gx", ms=ms, tflops=2.0 * TB * H4 * D / ms / 1e9)
+    ms = _time_ms(lambda: dG @ W)
+    _emit("gemm2_time", what="cuBLAS dX", ms=ms, tflops=2.0 * TB * H4 * D / ms / 1e9)
+    ms = _time_ms(lambda: torch.addmm(gw, dG.t(), X, out_dtype=torch.float32, out=gw))
+    _emit("gemm2_time", what="cuBLAS dW", ms=ms, tflops=2.0 * TB * H4 * D / ms / 1e9)
+    R = dG[:, :256].float().t() @ X.float()
+    gw.zero_()
+    E.gemm2(dG, X, out=gw, a_mn=True, b_mn=True, accumulate=True)
+    _emit("gemm2_dw_check", rel_err=float((gw[:256] - R).abs().max() / R.abs().max()))
 
 
 def _seq_case(T, B, H, D, check_bwd=True, time_it=False):
@@ -319,16 +354,6 @@ def check_seq_tiles():
               dh0_maxdiff=float((dh0 - ref[2]).abs().max()))
 
 
-def check_umma():
-    import torch
-    from lstm_tensorspark_b200.ops.cuda_ext import ext
-    E = ext()
-    for mode in (0, 1, 2, 3, 4):
-        for (M, N) in ((128, 64), (128, 128), (128, 256)):
-            out = E.umma_bench(M, N, 4000, mode).cpu()
-            _emit("umma", mode=mode, M=M, N=N, cycles_per_mma=float(out[0]) / float(out[1]), cycles_per_group_of_4=4 * float(out[0]) / float(out[1]))
-
-
 def check_seq_h2048():
     """Streamed-weights variant (BASELINE.json config 4 shape: H = 2048, B = 64)."""
     _seq_case(6, 64, 2048, 256, check_bwd=True, time_it=True)
@@ -358,7 +383,7 @@ def check_iris_gpu():
     _emit("iris_gpu_standalone", rc=r.returncode, tail=(r.stdout + r.stderr)[-600:])
 
 
-CHECKS = {"seq_h2048": check_seq_h2048, "bwd_tune": check_bwd_tune, "skew": check_skew, "seq_tiles": check_seq_tiles, "umma": check_umma, "seq_tune": check_seq_tune, "env": check_env, "simple": check_simple, "gemm": check_gemm, "generic": check_generic, "seq_small": check_seq_small,
+CHECKS = {"gemm2": check_gemm2, "seq_h2048": check_seq_h2048, "bwd_tune": check_bwd_tune, "skew": check_skew, "seq_tiles": check_seq_tiles, "seq_tune": check_seq_tune, "env": check_env, "simple": check_simple, "generic": check_generic, "seq_small": check_seq_small,
           "seq_big": check_seq_big, "engine": check_engine, "iris_gpu": check_iris_gpu}
 
 

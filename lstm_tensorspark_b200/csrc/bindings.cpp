@@ -5,6 +5,7 @@
 #include <torch/extension.h>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAException.h>
 #include <cuda_runtime.h>
 
 #include <optional>
@@ -25,20 +26,25 @@ int ts_head_xent(const void*, const float*, const float*, const long long*, floa
                  int, cudaStream_t);
 int ts_xent_rows(const float*, const long long*, float*, float*, int*, int, int, cudaStream_t);
 int ts_flat_adam(float*, const float*, float*, float*, void*, long long, float, float, float, float, float, float,
-                 cudaStream_t, int*);
-int ts_flat_sgd(float*, const float*, void*, long long, float, float, float, cudaStream_t);
+                 cudaStream_t, int*, long long);
+int ts_flat_sgd(float*, const float*, void*, long long, float, float, float, cudaStream_t, long long);
 int ts_cast_bf16(const float*, void*, long long, cudaStream_t);
 int ts_fused_allreduce(const unsigned long long*, unsigned long long, unsigned long long, unsigned long long, float*,
                        float*, unsigned int*, int*, long long, int, int, int, int, int, int, float, float, float, float,
-                       float, double, cudaStream_t, int*);
+                       float, double, cudaStream_t, int*, long long, int, int);
 int ts_ar_max_blocks();
 int ts_ar_flag_words();
-int ts_gemm_bf16_tn(const void*, const void*, void*, const float*, int, int, int, int, int, int, cudaStream_t);
+int ts_head_fwd_tc(const void*, int, const float*, const float*, const long long*, float*, float*, float*, int*, int, int, int, cudaStream_t);
+int ts_head_logits_generic(const void*, const float*, const float*, float*, int, int, int, int, cudaStream_t);
+int ts_head_bwd(const void*, const float*, const float*, const float*, void*, float*, float*, int, int, int, int, int, cudaStream_t);
+int ts_gemm_generic(const void*, const void*, void*, const float*, int, int, int, long long, long long, long long, long long, long long,
+                    int, int, int, float, cudaStream_t);
+int ts_gemm2(const void*, const void*, void*, const float*, int, int, int, int, int, int, int, int, int, int, int, int, int,
+             const unsigned int*, unsigned int, int, int*, cudaStream_t);
 int ts_lstm_seq_fwd(const void*, const void*, const float*, const void*, const float*, void*, const float*, void*, void*, int,
                     int, int, unsigned int*, int, cudaStream_t, const void*);
 int ts_lstm_seq_bwd(const void*, const void*, const void*, const float*, const void*, float*, float*, void*, void*, int,
                     int, int, unsigned int*, int, cudaStream_t);
-int ts_umma_bench(int, int, int, int, long long*, cudaStream_t);
 const char* ts_last_error();
 }
 
@@ -95,6 +101,16 @@ Tensor colsum_bf16(const Tensor& x) {
   auto out = torch::zeros({x.size(1)}, x.options().dtype(torch::kFloat32));
   check(ts_colsum_bf16(x.data_ptr(), out.data_ptr<float>(), (int)x.size(0), (int)x.size(1), stream()), "colsum_bf16");
   return out;
+}
+
+// column sums accumulated into an existing fp32 [cols] tensor (zero_first: overwrite instead of accumulate)
+void colsum_bf16_into(const Tensor& x, Tensor out, bool zero_first) {
+  chk_cuda(x, "x"); chk_cuda(out, "out");
+  TORCH_CHECK(x.dim() == 2 && is_bf16(x) && x.size(1) % 256 == 0 && out.scalar_type() == torch::kFloat32 && out.numel() == x.size(1),
+              "colsum_bf16_into: bf16 [rows, cols % 256 == 0] -> fp32 [cols]");
+  c10::cuda::CUDAGuard g(x.device());
+  if (zero_first) C10_CUDA_CHECK(cudaMemsetAsync(out.data_ptr(), 0, sizeof(float) * out.numel(), stream()));
+  check(ts_colsum_bf16(x.data_ptr(), out.data_ptr<float>(), (int)x.size(0), (int)x.size(1), stream()), "colsum_bf16_into");
 }
 
 // ---- generic LSTM cell epilogue -------------------------------------------------------------------------
@@ -159,22 +175,66 @@ std::vector<Tensor> xent_rows(const Tensor& logits, const Tensor& labels) {
   return {dlogits, loss, correct};
 }
 
+// Tensor-core head (csrc/head_tc.cu): bf16 h [B,H] (row pitch = stride(0)), fp32 W [H,C] / bias [C] -> logits, dlogits, loss sum,
+// correct count.  Shapes the tcgen05 kernel does not take (fp32 h, C > 256, weight image > smem) run head_logits_generic +
+// xent_rows - our own kernels, never a library GEMM.
+std::vector<Tensor> head_fwd(const Tensor& h, const Tensor& W, const Tensor& bias, const Tensor& labels) {
+  TORCH_CHECK(h.is_cuda() && h.dim() == 2 && h.stride(1) == 1, "head_fwd: h [B,H] with unit inner stride");
+  chk_cuda(W, "W"); chk_cuda(bias, "bias"); chk_cuda(labels, "labels");
+  c10::cuda::CUDAGuard g(h.device());
+  const int B = h.size(0), H = h.size(1), C = W.size(1);
+  TORCH_CHECK(W.size(0) == H && W.scalar_type() == torch::kFloat32 && bias.scalar_type() == torch::kFloat32, "head W/b");
+  TORCH_CHECK(labels.scalar_type() == torch::kInt64 && labels.numel() == B, "labels int64 [B]");
+  auto fo = torch::TensorOptions().device(h.device()).dtype(torch::kFloat32);
+  auto logits = torch::empty({B, C}, fo), dlogits = torch::empty({B, C}, fo);
+  auto loss = torch::zeros({1}, fo);
+  auto correct = torch::zeros({1}, fo.dtype(torch::kInt32));
+  int rc = -1;
+  if (h.scalar_type() == torch::kBFloat16)
+    rc = ts_head_fwd_tc(h.data_ptr(), (int)h.stride(0), W.data_ptr<float>(), bias.data_ptr<float>(), (const long long*)labels.data_ptr<int64_t>(),
+                        logits.data_ptr<float>(), dlogits.data_ptr<float>(), loss.data_ptr<float>(), correct.data_ptr<int>(), B, H, C, stream());
+  if (rc == -1) {
+    auto hc = h.contiguous();
+    check(ts_head_logits_generic(hc.data_ptr(), W.data_ptr<float>(), bias.data_ptr<float>(), logits.data_ptr<float>(), B, H, C, is_bf16(hc), stream()),
+          "head_logits_generic");
+    check(ts_xent_rows(logits.data_ptr<float>(), (const long long*)labels.data_ptr<int64_t>(), dlogits.data_ptr<float>(),
+                       loss.data_ptr<float>(), correct.data_ptr<int>(), B, C, stream()), "xent_rows");
+  } else {
+    check(rc, "head_fwd_tc");
+  }
+  return {logits, dlogits, loss, correct};
+}
+
+// dh = (dloss * dlogits) W^T [B,H] (dtype of h), dW (+)= h^T (dloss * dlogits) [H,C], db (+)= column sums: one launch.
+Tensor head_bwd(const Tensor& h, const Tensor& W, const Tensor& dlogits, const std::optional<Tensor>& dloss, Tensor dW, Tensor db,
+                bool accumulate) {
+  chk_cuda(h, "h"); chk_cuda(W, "W"); chk_cuda(dlogits, "dlogits"); chk_cuda(dW, "dW"); chk_cuda(db, "db");
+  c10::cuda::CUDAGuard g(h.device());
+  const int B = h.size(0), H = h.size(1), C = W.size(1);
+  TORCH_CHECK(dW.scalar_type() == torch::kFloat32 && db.scalar_type() == torch::kFloat32 && dW.numel() == (int64_t)H * C && db.numel() == C, "head_bwd: dW/db");
+  TORCH_CHECK(dlogits.scalar_type() == torch::kFloat32 && dlogits.numel() == (int64_t)B * C, "head_bwd: dlogits fp32 [B,C]");
+  auto dh = torch::empty_like(h);
+  check(ts_head_bwd(h.data_ptr(), W.data_ptr<float>(), dlogits.data_ptr<float>(), fptr(dloss), dh.data_ptr(), dW.data_ptr<float>(),
+                    db.data_ptr<float>(), B, H, C, is_bf16(h), accumulate ? 1 : 0, stream()), "head_bwd");
+  return dh;
+}
+
 // ---- optimizer ----------------------------------------------------------------------------------------------
 void flat_adam(Tensor p, const Tensor& g, Tensor m, Tensor v, std::optional<Tensor> shadow, double lr_t, double b1,
-               double b2, double eps, double wd, double gscale, std::optional<Tensor> step_dev) {
+               double b2, double eps, double wd, double gscale, std::optional<Tensor> step_dev, int64_t wd_numel) {
   chk_cuda(p, "p"); chk_cuda(g, "g"); chk_cuda(m, "m"); chk_cuda(v, "v");
   c10::cuda::CUDAGuard gd(p.device());
   TORCH_CHECK(p.numel() == g.numel() && p.numel() == m.numel() && p.numel() == v.numel(), "numel mismatch");
   check(ts_flat_adam(p.data_ptr<float>(), g.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(),
                      shadow.has_value() ? shadow->data_ptr() : nullptr, p.numel(), lr_t, b1, b2, eps, wd, gscale, stream(),
-                     step_dev.has_value() ? step_dev->data_ptr<int>() : nullptr),
+                     step_dev.has_value() ? step_dev->data_ptr<int>() : nullptr, (long long)wd_numel),
         "flat_adam");
 }
-void flat_sgd(Tensor p, const Tensor& g, std::optional<Tensor> shadow, double lr, double wd, double gscale) {
+void flat_sgd(Tensor p, const Tensor& g, std::optional<Tensor> shadow, double lr, double wd, double gscale, int64_t wd_numel) {
   chk_cuda(p, "p"); chk_cuda(g, "g");
   c10::cuda::CUDAGuard gd(p.device());
   check(ts_flat_sgd(p.data_ptr<float>(), g.data_ptr<float>(), shadow.has_value() ? shadow->data_ptr() : nullptr,
-                    p.numel(), lr, wd, gscale, stream()), "flat_sgd");
+                    p.numel(), lr, wd, gscale, stream(), (long long)wd_numel), "flat_sgd");
 }
 void cast_bf16(const Tensor& p, Tensor shadow) {
   chk_cuda(p, "p"); chk_cuda(shadow, "shadow");
@@ -188,7 +248,7 @@ void cast_bf16(const Tensor& p, Tensor shadow) {
 void fused_allreduce(const Tensor& ptrs, int64_t mc_in, int64_t mc_param, int64_t mc_shadow, std::optional<Tensor> m,
                      std::optional<Tensor> v, Tensor epochs, Tensor err, int64_t n, int64_t rank, int64_t world,
                      int64_t mode, bool two_shot, bool multicast, int64_t blocks, double lr, double b1, double b2,
-                     double eps, double wd, double timeout_s, std::optional<Tensor> step_dev) {
+                     double eps, double wd, double timeout_s, std::optional<Tensor> step_dev, int64_t wd_numel, bool bump_step, bool pdl) {
   TORCH_CHECK(!ptrs.is_cuda() && ptrs.scalar_type() == torch::kInt64 && ptrs.numel() == 4 * world, "ptrs: cpu int64 [4,world]");
   chk_cuda(epochs, "epochs"); chk_cuda(err, "err");
   c10::cuda::CUDAGuard gd(epochs.device());
@@ -197,20 +257,56 @@ void fused_allreduce(const Tensor& ptrs, int64_t mc_in, int64_t mc_param, int64_
                            m.has_value() ? m->data_ptr<float>() : nullptr, v.has_value() ? v->data_ptr<float>() : nullptr,
                            (unsigned int*)epochs.data_ptr<int>(), err.data_ptr<int>(), n, (int)rank, (int)world, (int)mode,
                            two_shot ? 1 : 0, multicast ? 1 : 0, (int)blocks, lr, b1, b2, eps, wd, timeout_s, stream(),
-                           step_dev.has_value() ? step_dev->data_ptr<int>() : nullptr),
+                           step_dev.has_value() ? step_dev->data_ptr<int>() : nullptr, (long long)wd_numel, bump_step ? 1 : 0, pdl ? 1 : 0),
         "fused_allreduce");
 }
 
-// ---- tcgen05 GEMM: C[M,N] = A[M,K] * B[N,K]^T (+bias[N]) ; bf16 in, fp32 accumulate in TMEM --------------------
-Tensor gemm_bf16_tn(const Tensor& A, const Tensor& B, const std::optional<Tensor>& bias, bool out_fp32, int64_t variant) {
-  chk_cuda(A, "A"); chk_cuda(B, "B");
+// ---- general tcgen05 GEMM (csrc/gemm2_tcgen05.cu): C[M,N] (=|+=) op(A)·op(B) (+bias) ------------------------------------
+// a_mn = false: A is [M,K] (K contiguous); true: A is [K,M] (M contiguous).  b_mn = false: B is [N,K]; true: B is [K,N].
+// out: optional preallocated C (fp32 for accumulate = C += A·B, or any mode); out_fp32 selects the dtype of a fresh C.
+Tensor gemm2(const Tensor& A, const Tensor& B, const std::optional<Tensor>& bias, std::optional<Tensor> out, bool a_mn, bool b_mn,
+             bool out_fp32, bool accumulate, int64_t ctas, int64_t bn, int64_t max_ctas, const std::optional<Tensor>& gate,
+             int64_t gate_target, int64_t gate_rows, const std::optional<Tensor>& gate_err) {
+  TORCH_CHECK(A.is_cuda() && B.is_cuda(), "gemm2: CUDA tensors");
+  TORCH_CHECK(A.scalar_type() == torch::kBFloat16 && B.scalar_type() == torch::kBFloat16, "gemm2: A/B must be bf16");
+  TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && A.stride(1) == 1 && B.stride(1) == 1, "gemm2: 2-D operands with unit inner stride");
   c10::cuda::CUDAGuard gd(A.device());
-  TORCH_CHECK(A.scalar_type() == torch::kBFloat16 && B.scalar_type() == torch::kBFloat16, "A/B must be bf16");
-  TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && A.size(1) == B.size(1), "A [M,K], B [N,K]");
-  int M = A.size(0), K = A.size(1), N = B.size(0);
-  auto C = torch::empty({M, N}, A.options().dtype(out_fp32 ? torch::kFloat32 : torch::kBFloat16));
-  check(ts_gemm_bf16_tn(A.data_ptr(), B.data_ptr(), C.data_ptr(), fptr(bias), M, N, K, out_fp32 ? 1 : 0, (int)variant,
-                        A.device().index(), stream()), "gemm_bf16_tn");
+  const int M = a_mn ? A.size(1) : A.size(0), K = a_mn ? A.size(0) : A.size(1);
+  const int N = b_mn ? B.size(1) : B.size(0), Kb = b_mn ? B.size(0) : B.size(1);
+  TORCH_CHECK(K == Kb, "gemm2: contraction sizes differ (", K, " vs ", Kb, ")");
+  Tensor C;
+  if (out.has_value()) {
+    C = *out;
+    TORCH_CHECK(C.is_cuda() && C.dim() == 2 && C.size(0) == M && C.size(1) == N && C.stride(1) == 1, "gemm2: out must be [M,N]");
+    TORCH_CHECK(C.scalar_type() == (out_fp32 || accumulate ? torch::kFloat32 : torch::kBFloat16), "gemm2: out dtype");
+  } else {
+    TORCH_CHECK(!accumulate, "gemm2: accumulate needs out=");
+    C = torch::empty({M, N}, A.options().dtype(out_fp32 ? torch::kFloat32 : torch::kBFloat16));
+  }
+  const int out_mode = accumulate ? 2 : (C.scalar_type() == torch::kFloat32 ? 1 : 0);
+  const unsigned int* gp = nullptr;
+  if (gate.has_value()) { TORCH_CHECK(gate->is_cuda() && gate->scalar_type() == torch::kInt32, "gemm2: gate int32 cuda"); gp = (const unsigned int*)gate->data_ptr<int>(); }
+  check(ts_gemm2(A.data_ptr(), B.data_ptr(), C.data_ptr(), fptr(bias), M, N, K, (int)A.stride(0), (int)B.stride(0), (int)C.stride(0),
+                 a_mn ? 1 : 0, b_mn ? 1 : 0, out_mode, (int)ctas, (int)bn, A.device().index(), (int)max_ctas, gp, (unsigned int)gate_target,
+                 (int)gate_rows, gate_err.has_value() ? gate_err->data_ptr<int>() : nullptr, stream()), "gemm2");
+  return C;
+}
+
+// ---- any-shape CUDA-core GEMM (csrc/gemm_generic.cu): C = beta*C + A·B, A [M,K] / B [K,N] with arbitrary strides --------------
+Tensor gemm_generic(const Tensor& A, const Tensor& B, const std::optional<Tensor>& bias, std::optional<Tensor> out, bool out_fp32, double beta) {
+  TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.dim() == 2 && B.dim() == 2 && A.size(1) == B.size(0), "gemm_generic: A [M,K] x B [K,N]");
+  c10::cuda::CUDAGuard gd(A.device());
+  const int M = A.size(0), K = A.size(1), N = B.size(1);
+  Tensor C;
+  if (out.has_value()) {
+    C = *out;
+    TORCH_CHECK(C.is_cuda() && C.dim() == 2 && C.size(0) == M && C.size(1) == N && C.stride(1) == 1, "gemm_generic: out [M,N]");
+  } else {
+    TORCH_CHECK(beta == 0.0, "gemm_generic: beta needs out=");
+    C = torch::empty({M, N}, A.options().dtype(out_fp32 ? torch::kFloat32 : A.scalar_type()));
+  }
+  check(ts_gemm_generic(A.data_ptr(), B.data_ptr(), C.data_ptr(), fptr(bias), M, N, K, A.stride(0), A.stride(1), B.stride(0), B.stride(1),
+                        C.stride(0), is_bf16(A), is_bf16(B), is_bf16(C), (float)beta, stream()), "gemm_generic");
   return C;
 }
 
@@ -257,12 +353,6 @@ std::vector<Tensor> lstm_seq_bwd(const std::optional<Tensor>& dh_seq, const Tens
   return {dpre, dh0, dc0};
 }
 
-Tensor umma_bench(int64_t M, int64_t N, int64_t iters, int64_t mode) {
-  auto out = torch::zeros({2}, torch::TensorOptions().device(torch::kCUDA).dtype(torch::kInt64));
-  check(ts_umma_bench((int)M, (int)N, (int)iters, (int)mode, (long long*)out.data_ptr<int64_t>(), stream()), "umma_bench");
-  return out;
-}
-
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -271,22 +361,33 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("transpose01", &transpose01);
   m.def("transpose2d", &transpose2d);
   m.def("colsum_bf16", &colsum_bf16);
+  m.def("colsum_bf16_into", &colsum_bf16_into);
   m.def("lstm_seq_cluster_probe", [](int64_t c) { return ts_lstm_seq_cluster_probe((int)c); });
   m.def("lstm_pointwise_bwd", &lstm_pointwise_bwd);
   m.def("head_xent", &head_xent);
   m.def("xent_rows", &xent_rows);
+  m.def("head_fwd", &head_fwd);
+  m.def("head_bwd", &head_bwd, py::arg("h"), py::arg("W"), py::arg("dlogits"), py::arg("dloss"), py::arg("dW"), py::arg("db"),
+        py::arg("accumulate") = false);
   m.def("flat_adam", &flat_adam, py::arg("p"), py::arg("g"), py::arg("m"), py::arg("v"), py::arg("shadow"), py::arg("lr_t"),
-        py::arg("b1"), py::arg("b2"), py::arg("eps"), py::arg("wd"), py::arg("gscale"), py::arg("step_dev") = py::none());
-  m.def("flat_sgd", &flat_sgd);
+        py::arg("b1"), py::arg("b2"), py::arg("eps"), py::arg("wd"), py::arg("gscale"), py::arg("step_dev") = py::none(),
+        py::arg("wd_numel") = -1);
+  m.def("flat_sgd", &flat_sgd, py::arg("p"), py::arg("g"), py::arg("shadow"), py::arg("lr"), py::arg("wd"), py::arg("gscale"),
+        py::arg("wd_numel") = -1);
   m.def("cast_bf16", &cast_bf16);
   m.def("fused_allreduce", &fused_allreduce, py::arg("ptrs"), py::arg("mc_in"), py::arg("mc_param"), py::arg("mc_shadow"), py::arg("m"),
         py::arg("v"), py::arg("epochs"), py::arg("err"), py::arg("n"), py::arg("rank"), py::arg("world"), py::arg("mode"),
         py::arg("two_shot"), py::arg("multicast"), py::arg("blocks"), py::arg("lr"), py::arg("b1"), py::arg("b2"), py::arg("eps"),
-        py::arg("wd"), py::arg("timeout_s"), py::arg("step_dev") = py::none());
+        py::arg("wd"), py::arg("timeout_s"), py::arg("step_dev") = py::none(), py::arg("wd_numel") = -1, py::arg("bump_step") = true,
+        py::arg("pdl") = false);
   m.def("ar_max_blocks", []() { return ts_ar_max_blocks(); });
   m.def("ar_flag_words", []() { return ts_ar_flag_words(); });
-  m.def("gemm_bf16_tn", &gemm_bf16_tn);
-  m.def("umma_bench", &umma_bench);
+  m.def("gemm_generic", &gemm_generic, py::arg("A"), py::arg("B"), py::arg("bias") = py::none(), py::arg("out") = py::none(),
+        py::arg("out_fp32") = false, py::arg("beta") = 0.0);
+  m.def("gemm2", &gemm2, py::arg("A"), py::arg("B"), py::arg("bias") = py::none(), py::arg("out") = py::none(), py::arg("a_mn") = false,
+        py::arg("b_mn") = false, py::arg("out_fp32") = false, py::arg("accumulate") = false, py::arg("ctas") = 2, py::arg("bn") = 256,
+        py::arg("max_ctas") = 0, py::arg("gate") = py::none(), py::arg("gate_target") = 0, py::arg("gate_rows") = 0,
+        py::arg("gate_err") = py::none());
   m.def("lstm_seq_fwd", &lstm_seq_fwd, py::arg("gx"), py::arg("w_h"), py::arg("bias"), py::arg("h0"), py::arg("c0"),
         py::arg("sync_ws"), py::arg("cluster") = 0, py::arg("dbg") = py::none());
   m.def("lstm_seq_bwd", &lstm_seq_bwd, py::arg("dh_seq"), py::arg("w_hT"), py::arg("act"), py::arg("c_seq"), py::arg("dhT"),

@@ -44,6 +44,7 @@ struct ARArgs {
   int* err;                    // local error flag (1 = barrier timeout)
   int* step_dev;               // Adam: device-resident step counter (graph-replay safe); null -> lr is already corrected
   long long n4;                // message length in float4
+  long long wd_n4;             // weight decay applies to float4 indices below this (the LSTM variables)
   int rank, world;
   float inv_world, lr, b1, b2, eps, wd;
   unsigned long long timeout_ns;
@@ -116,16 +117,17 @@ TS_DEVICE float4 apply_update(const ARArgs& a, float4 sum, long long i, float4 w
   g.x = sum.x * a.inv_world; g.y = sum.y * a.inv_world; g.z = sum.z * a.inv_world; g.w = sum.w * a.inv_world;
   if (kMode == MODE_AVG) return g;
   float* wp = &w.x; float* gp = &g.x;
+  const float wd = i < a.wd_n4 ? a.wd : 0.f;
   if (kMode == MODE_SGD) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) wp[k] -= lr * (gp[k] + a.wd * wp[k]);
+    for (int k = 0; k < 4; ++k) wp[k] -= lr * (gp[k] + wd * wp[k]);
     return w;
   }
   float4 mv = reinterpret_cast<float4*>(a.m)[i], vv = reinterpret_cast<float4*>(a.v)[i];
   float* mp = &mv.x; float* vp = &vv.x;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    float gg = gp[k] + a.wd * wp[k];
+    float gg = gp[k] + wd * wp[k];
     mp[k] = a.b1 * mp[k] + (1.f - a.b1) * gg;
     vp[k] = a.b2 * vp[k] + (1.f - a.b2) * gg * gg;
     wp[k] -= lr * mp[k] / (sqrtf(vp[k]) + a.eps);        // lr is the bias-corrected lr_t
@@ -223,15 +225,28 @@ __global__ void __launch_bounds__(kThreads) ar_one_shot_kernel(const __grid_cons
   if (threadIdx.x == 0) a.epochs[blockIdx.x] = epoch;
 }
 
+// pdl: programmatic dependent launch - the kernel may start while the PREVIOUS kernel of the stream is still running (as soon
+// as all of that kernel's CTAs are resident and have executed griddepcontrol.launch_dependents).  Used to run a gradient
+// bucket's allreduce + update on the ~20 SMs a persistent LSTM recurrence kernel leaves idle; it does not read anything the
+// previous kernel writes, so it never executes griddepcontrol.wait.
+template <typename K>
+int launch_k(K kern, const ARArgs& a, int blocks, int pdl, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return (int)cudaLaunchKernelEx(&cfg, kern, a);
+}
+
 template <int kMode>
-int launch_mode(const ARArgs& a, int two_shot, int multicast, int blocks, cudaStream_t st) {
+int launch_mode(const ARArgs& a, int two_shot, int multicast, int blocks, int pdl, cudaStream_t st) {
   if (two_shot) {
-    if (multicast) ar_two_shot_kernel<kMode, true><<<blocks, kThreads, 0, st>>>(a);
-    else ar_two_shot_kernel<kMode, false><<<blocks, kThreads, 0, st>>>(a);
-  } else {
-    ar_one_shot_kernel<kMode><<<blocks, kThreads, 0, st>>>(a);
+    if (multicast) return launch_k(ar_two_shot_kernel<kMode, true>, a, blocks, pdl, st);
+    return launch_k(ar_two_shot_kernel<kMode, false>, a, blocks, pdl, st);
   }
-  return (int)cudaGetLastError();
+  return launch_k(ar_one_shot_kernel<kMode>, a, blocks, pdl, st);
 }
 
 }  // namespace
@@ -241,7 +256,7 @@ extern "C" int ts_fused_allreduce(const unsigned long long* ptrs, unsigned long 
                                   unsigned long long mc_shadow, float* m, float* v, unsigned int* epochs, int* err,
                                   long long n, int rank, int world, int mode, int two_shot, int multicast, int blocks,
                                   float lr, float b1, float b2, float eps, float wd, double timeout_s,
-                                  cudaStream_t st, int* step_dev) {
+                                  cudaStream_t st, int* step_dev, long long wd_n, int bump_step, int pdl) {
   if (world > kMaxRanks || world < 1 || n % 4 != 0) return -2;
   if (blocks > kMaxBlocks) blocks = kMaxBlocks;
   if (blocks < 1) blocks = 1;
@@ -254,15 +269,16 @@ extern "C" int ts_fused_allreduce(const unsigned long long* ptrs, unsigned long 
   }
   a.mc_in = (float*)mc_in; a.mc_param = (float*)mc_param; a.mc_shadow = (__nv_bfloat16*)mc_shadow;
   a.m = m; a.v = v; a.epochs = epochs; a.err = err; a.step_dev = (mode == MODE_ADAM) ? step_dev : nullptr;
-  if (a.step_dev) ar_inc_step_kernel<<<1, 1, 0, st>>>(a.step_dev);
+  if (a.step_dev && bump_step) ar_inc_step_kernel<<<1, 1, 0, st>>>(a.step_dev);     // once per optimizer step, not per bucket
+  a.wd_n4 = wd_n < 0 ? n / 4 : wd_n / 4;
   a.n4 = n / 4; a.rank = rank; a.world = world; a.inv_world = 1.0f / (float)world;
   a.lr = lr; a.b1 = b1; a.b2 = b2; a.eps = eps; a.wd = wd;
   a.timeout_ns = (unsigned long long)(timeout_s * 1e9);
   if (multicast && (!mc_in || !mc_param)) multicast = 0;
   switch (mode) {
-    case MODE_AVG: return launch_mode<MODE_AVG>(a, two_shot, multicast, blocks, st);
-    case MODE_SGD: return launch_mode<MODE_SGD>(a, two_shot, multicast, blocks, st);
-    case MODE_ADAM: return launch_mode<MODE_ADAM>(a, two_shot, multicast, blocks, st);
+    case MODE_AVG: return launch_mode<MODE_AVG>(a, two_shot, multicast, blocks, pdl, st);
+    case MODE_SGD: return launch_mode<MODE_SGD>(a, two_shot, multicast, blocks, pdl, st);
+    case MODE_ADAM: return launch_mode<MODE_ADAM>(a, two_shot, multicast, blocks, pdl, st);
   }
   return -3;
 }

@@ -232,6 +232,10 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
   SeqSmem* ss = reinterpret_cast<SeqSmem*>(smem_x + (kCluster ? kTiles * kXchgBytes : 0));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Programmatic dependent launch: a kernel queued behind this one WITH the PDL attribute (the fused allreduce + update of a
+  // gradient bucket that is already complete) may start once every CTA of this grid is resident - it then runs on the SMs
+  // this persistent grid leaves idle instead of after it.  No effect on ordinary launches.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int mb0 = (blockIdx.x / p.tiles_n) * kTiles;          // first batch tile of this CTA
   const int in_mb = blockIdx.x % p.tiles_n;
   const uint32_t crank = kCluster ? cluster_ctarank() : 0;

@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) flat_adam_kernel(float4* __restrict__ p, 
                                                         float4* __restrict__ m, float4* __restrict__ v,
                                                         uint2* __restrict__ shadow, size_t n4, float lr_t, float b1,
                                                         float b2, float eps, float wd, float gscale,
-                                                        const int* __restrict__ step_dev) {
+                                                        const int* __restrict__ step_dev, size_t wd_n4) {
   if (step_dev != nullptr) {
     const float t = (float)(*step_dev);
     lr_t = lr_t * sqrtf(1.f - powf(b2, t)) / (1.f - powf(b1, t));      // lr_t arrives as the base learning rate
@@ -32,9 +32,10 @@ __global__ void __launch_bounds__(256) flat_adam_kernel(float4* __restrict__ p, 
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 pv = p[i], gv = g[i], mv = m[i], vv = v[i];
     float* pp = &pv.x; float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
+    const float wdi = i < wd_n4 ? wd : 0.f;        // the L2 term of create_variable covers the LSTM variables only (K12)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      float gg = gp[k] * gscale + wd * pp[k];
+      float gg = gp[k] * gscale + wdi * pp[k];
       mp[k] = b1 * mp[k] + (1.f - b1) * gg;
       vp[k] = b2 * vp[k] + (1.f - b2) * gg * gg;
       pp[k] -= lr_t * mp[k] / (sqrtf(vp[k]) + eps);
@@ -46,14 +47,15 @@ __global__ void __launch_bounds__(256) flat_adam_kernel(float4* __restrict__ p, 
 
 __global__ void __launch_bounds__(256) flat_sgd_kernel(float4* __restrict__ p, const float4* __restrict__ g,
                                                        uint2* __restrict__ shadow, size_t n4, float lr, float wd,
-                                                       float gscale) {
+                                                       float gscale, size_t wd_n4) {
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 pv = p[i], gv = g[i];
-    pv.x -= lr * (gv.x * gscale + wd * pv.x);
-    pv.y -= lr * (gv.y * gscale + wd * pv.y);
-    pv.z -= lr * (gv.z * gscale + wd * pv.z);
-    pv.w -= lr * (gv.w * gscale + wd * pv.w);
+    const float wdi = i < wd_n4 ? wd : 0.f;
+    pv.x -= lr * (gv.x * gscale + wdi * pv.x);
+    pv.y -= lr * (gv.y * gscale + wdi * pv.y);
+    pv.z -= lr * (gv.z * gscale + wdi * pv.z);
+    pv.w -= lr * (gv.w * gscale + wdi * pv.w);
     p[i] = pv;
     if (shadow) shadow[i] = pack_bf16x4(pv);
   }
@@ -74,20 +76,20 @@ int grid_for(size_t n4) {
 }  // namespace
 
 extern "C" int ts_flat_adam(float* p, const float* g, float* m, float* v, void* shadow, long long n, float lr_t,
-                            float b1, float b2, float eps, float wd, float gscale, cudaStream_t st, int* step_dev) {
+                            float b1, float b2, float eps, float wd, float gscale, cudaStream_t st, int* step_dev, long long wd_n) {
   if (n % 4) return -2;
   size_t n4 = (size_t)n / 4;
   if (step_dev) inc_step_kernel<<<1, 1, 0, st>>>(step_dev);
   flat_adam_kernel<<<grid_for(n4), 256, 0, st>>>((float4*)p, (const float4*)g, (float4*)m, (float4*)v, (uint2*)shadow,
-                                                 n4, lr_t, b1, b2, eps, wd, gscale, step_dev);
+                                                 n4, lr_t, b1, b2, eps, wd, gscale, step_dev, wd_n < 0 ? n4 : (size_t)wd_n / 4);
   return (int)cudaGetLastError();
 }
 
 extern "C" int ts_flat_sgd(float* p, const float* g, void* shadow, long long n, float lr, float wd, float gscale,
-                           cudaStream_t st) {
+                           cudaStream_t st, long long wd_n) {
   if (n % 4) return -2;
   size_t n4 = (size_t)n / 4;
-  flat_sgd_kernel<<<grid_for(n4), 256, 0, st>>>((float4*)p, (const float4*)g, (uint2*)shadow, n4, lr, wd, gscale);
+  flat_sgd_kernel<<<grid_for(n4), 256, 0, st>>>((float4*)p, (const float4*)g, (uint2*)shadow, n4, lr, wd, gscale, wd_n < 0 ? n4 : (size_t)wd_n / 4);
   return (int)cudaGetLastError();
 }
 

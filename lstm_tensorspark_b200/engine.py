@@ -17,7 +17,7 @@ import torch
 
 from .config import Config
 from .models.classifier import SequenceClassifier
-from .models.recurrent.lstm import clear_weight_decay_collection
+from .models.recurrent.lstm import clear_weight_decay_collection, weight_decay_collection
 from .ops import functional as F
 from .ops.optim import FlatOptimizer
 from .parallel.comm import Communicator
@@ -51,19 +51,84 @@ class TrainEngine:
             self.optimizer = train_optimizer(cfg.learning_rate)(self.flat)
         else:
             self.optimizer = FlatOptimizer(self.flat, cfg.learning_rate, cfg.optimizer, weight_decay=0.0)
+        # K12: the optional L2 term of create_variable (/root/reference/src/models/recurrent/lstm.py:9-11) is folded into the
+        # update kernel (g + wd * w over the LSTM weight / bias segment) instead of an autograd term over 67 MB of weights;
+        # variables outside that segment that asked for decay (learned initial states) keep the autograd term
+        self.optimizer.weight_decay = float(cfg.weight_decay or 0.0)
+        self.optimizer.wd_numel = self.flat.lstm_numel
+        seg_ids = {id(p) for p in self.model.rnn.averaged_parameters()}
+        self._wd_in_kernel = [(v, fn, wd) for (v, fn, wd) in weight_decay_collection() if id(v) in seg_ids]
+        self._wd_autograd = [(v, fn, wd) for (v, fn, wd) in weight_decay_collection() if id(v) not in seg_ids]
         self.sync_grads = cfg.sync_mode == "grad_allreduce" and world_size > 1
+        self._bucket_plan = self._make_bucket_plan() if (self.sync_grads and hasattr(self.comm, "launch_bucket")
+                                                         and cfg.grad_buckets) else None
         self._graph = None
         self._static = None
         self.steps_done = 0
 
     # ---------------------------------------------------------------------------------------------------
+    def _make_bucket_plan(self):
+        """Gradient buckets in the order backward finishes them: [top layer (+ head)], ..., [layer 0].  A bucket = a
+        contiguous element range of the flat buffer + the parameters that must have been written before it may be synced.
+        (Reference counterpart: the one-shot reduceByKey over all weights, /root/reference/src/rnn.py:393-407 - here the sync
+        of the upper layers hides under the backward recurrence of the layers below.)"""
+        flat = self.flat
+        if not flat._direct:
+            return None
+        off = {id(p): o for p, o in zip(flat.params, flat.offsets)}
+        layers = list(self.model.rnn.layers)
+        starts = [off[id(l.w_x)] for l in layers] + [flat.lstm_numel]
+        others = [p for p in flat.params[len(self.model.rnn.averaged_parameters()):]]
+        others_direct = all(p.data_ptr() in flat._direct for p in others)
+        plan = []
+        for li in reversed(range(len(layers))):
+            lo, hi = starts[li], starts[li + 1]
+            need = [layers[li].w_x, layers[li].w_h, layers[li].bias]
+            if li == len(layers) - 1 and others_direct:
+                hi = flat.padded_numel                     # head weights / bias follow the last layer in the flat buffer
+                need = need + others
+            plan.append({"lo": lo, "hi": hi, "need": {p.data_ptr() for p in need}})
+        if not others_direct:
+            plan.append({"lo": flat.lstm_numel, "hi": flat.padded_numel, "need": None})    # autograd-accumulated: only final at the end
+        return plan
+
+    def _backward_with_buckets(self, loss: torch.Tensor):
+        from .ops import cuda_lstm
+        flat, comm, plan = self.flat, self.comm, self._bucket_plan
+        comm.begin_grad_step(flat, self.optimizer)
+        state = {"next": 0}
+
+        def ready():
+            # queue every leading bucket whose parameters have all been written; it is launched (PDL) right after the next
+            # persistent backward kernel of a lower layer, i.e. it overlaps that recurrence
+            while state["next"] < len(plan) - 1:
+                b = plan[state["next"]]
+                if b["need"] is None or (b["need"] & flat._stale):
+                    break
+                cuda_lstm.AFTER_SEQ_BWD.append(lambda b=b: comm.launch_bucket(b["lo"], b["hi"], pdl=True, blocks=self.cfg.grad_bucket_blocks))
+                state["next"] += 1
+
+        cuda_lstm.HOOKS["layer_grads_ready"] = ready
+        try:
+            loss.backward()
+        finally:
+            cuda_lstm.HOOKS["layer_grads_ready"] = None
+        flat.finalize_grads()
+        while cuda_lstm.AFTER_SEQ_BWD:                      # queued but no lower recurrence followed (generic path)
+            cuda_lstm.AFTER_SEQ_BWD.pop(0)()
+        for b in plan[state["next"]:]:
+            comm.launch_bucket(b["lo"], b["hi"])
+
     def _step_eager(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         self.flat.zero_grad()
         loss, _logits, _correct = self.model(x, y)
-        if self.cfg.weight_decay:
-            from .models.recurrent.lstm import weight_decay_terms
-            loss = loss + torch.stack(weight_decay_terms()).sum()
+        if self._wd_autograd:
+            loss = loss + torch.stack([fn(v) * wd for (v, fn, wd) in self._wd_autograd]).sum()
         loss.backward()
+        if self._wd_in_kernel:                 # reported total loss includes the L2 value; its gradient is applied by the update kernel
+            with torch.no_grad():
+                loss = loss.detach() + torch.stack([fn(v) * wd for (v, fn, wd) in self._wd_in_kernel]).sum()
+        self.flat.finalize_grads()
         if self.sync_grads:
             self.comm.grad_step_(self.flat, self.optimizer)
         else:

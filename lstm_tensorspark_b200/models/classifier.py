@@ -26,7 +26,11 @@ class DenseHead(nn.Module):
         self.bias = create_variable("bias", (num_classes,), initializer=init, device=device, generator=generator)
 
     def forward(self, h: torch.Tensor) -> torch.Tensor:
-        return h.reshape(h.shape[0], -1).float() @ self.weights + self.bias
+        h2 = h.reshape(h.shape[0], -1)
+        if h2.is_cuda and F.get_backend() != "torch":
+            from ..ops import cuda_gemm             # evaluation logits: our own GEMM kernels, no library call on the CUDA path
+            return cuda_gemm.matmul(h2, self.weights.detach().t(), bias=self.bias.detach().float(), out_dtype=torch.float32)
+        return h2.float() @ self.weights + self.bias
 
 
 class SequenceClassifier(nn.Module):
@@ -58,6 +62,10 @@ class SequenceClassifier(nn.Module):
         self.compute_dtype = dtype
         if dtype != torch.float32 and self.flat is not None:
             self.flat.ensure_shadow()
+            if self.flat.data.is_cuda and F.get_backend() != "torch":
+                # the CUDA ops write these gradients straight into the flat buffer (first write of a step overwrites):
+                # zero_grad() then has nothing to memset
+                self.flat.enable_direct_grads(self.rnn.averaged_parameters() + [self.head.weights, self.head.bias])
 
     def features(self, x: torch.Tensor) -> torch.Tensor:
         self.rnn.reset_state(x.shape[0])

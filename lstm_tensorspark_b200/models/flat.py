@@ -48,6 +48,11 @@ class FlatParams:
         self.data.zero_()
         self.grad.zero_()
         self.shadow: Optional[torch.Tensor] = None      # bf16 copy maintained by the optimizer kernel
+        # Lazy gradient zeroing (CUDA path): parameters whose gradients are WRITTEN by our kernels (first producer of a step
+        # overwrites, later ones accumulate) are only marked stale by zero_grad(); no 67 MB memset per step.
+        self._direct: set = set()                       # data_ptr of parameters with a direct gradient sink
+        self._direct_ids: set = set()                   # the same parameters by identity (addresses change on rebase)
+        self._stale: set = set()
         with torch.no_grad():
             for p, o in zip(params, self.offsets):
                 self.data[o:o + p.numel()].view_as(p).copy_(p.data)
@@ -57,6 +62,8 @@ class FlatParams:
         for p, o in zip(self.params, self.offsets):
             p.data = self.data[o:o + p.numel()].view(p.shape)
             p.grad = self.grad[o:o + p.numel()].view(p.shape)
+        if getattr(self, "_direct_ids", None):
+            self._refresh_direct()
 
     def rebase(self, new_data: torch.Tensor, new_grad: torch.Tensor):
         """Move storage (e.g. into symmetric memory) keeping values."""
@@ -91,8 +98,43 @@ class FlatParams:
         o = self.offsets[i]
         return self.ensure_shadow()[o:o + p.numel()].view(p.shape)
 
+    def enable_direct_grads(self, params: Sequence[nn.Parameter]):
+        """Declare parameters whose gradients the CUDA ops write straight into ``grad`` (see ``take_sink``)."""
+        self._direct_ids = {id(p) for p in params}
+        self._refresh_direct()
+
+    def _refresh_direct(self):
+        self._direct = {p.data_ptr() for p in self.params if id(p) in self._direct_ids}
+        self._stale = set()
+
     def zero_grad(self):
-        self.grad.zero_()
+        if not self._direct:
+            self.grad.zero_()
+            return
+        self._stale = set(self._direct)
+        for p in self.params:                           # everything autograd accumulates into (p.grad += g) still needs zeros
+            if p.data_ptr() not in self._direct:
+                p.grad.zero_()
+
+    def take_sink(self, addr: int) -> bool:
+        """A kernel is about to write the gradient of the parameter at ``addr``: returns True when it must ACCUMULATE
+        (something was already written this step), False when it must overwrite (first write after zero_grad)."""
+        if addr in self._stale:
+            self._stale.discard(addr)
+            return False
+        return True
+
+    def ensure_zeroed(self, addr: int):
+        """The gradient of ``addr`` is about to be accumulated by autograd (not by a direct kernel write)."""
+        if addr in self._stale:
+            self._stale.discard(addr)
+            i = next(k for k, q in enumerate(self.params) if q.data_ptr() == addr)
+            self.params[i].grad.zero_()
+
+    def finalize_grads(self):
+        """After backward: parameters that received no gradient this step hold zeros, not last step's values."""
+        for addr in list(self._stale):
+            self.ensure_zeroed(addr)
 
     def segment(self, scope: str) -> Tuple[int, int]:
         """Element range that is synchronised across replicas."""

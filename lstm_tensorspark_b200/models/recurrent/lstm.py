@@ -52,6 +52,11 @@ def weight_decay_terms():
     return [fn(v) * wd for (v, fn, wd) in _WEIGHT_DECAY_COLLECTION]
 
 
+def weight_decay_collection():
+    """``[(variable, loss_fn, coefficient)]`` registered by ``create_variable(..., weight_decay=)``."""
+    return list(_WEIGHT_DECAY_COLLECTION)
+
+
 def clear_weight_decay_collection():
     _WEIGHT_DECAY_COLLECTION.clear()
 

@@ -1,6 +1,7 @@
-"""CUDA head op: dense layer + softmax cross-entropy + accuracy in one launch (csrc/head_xent.cu);
-backward = two small library GEMMs on the dlogits the forward kernel already produced.
-Parity: /root/reference/src/rnn.py:214-221 (Dense1), :55-63 (loss), :84-92 (accuracy)."""
+"""CUDA head op: dense layer + softmax cross-entropy + accuracy in ONE launch on the tensor cores (csrc/head_tc.cu:
+TMA-fed tcgen05 tile, logits in TMEM, softmax / NLL / accuracy / dlogits in the epilogue) and the whole backward
+(dh, dW, db) in ONE launch that writes dW / db straight into the flat gradient buffer.
+Parity: /root/reference/src/rnn.py:214-221 (Dense1), :55-63 (loss), :84-92 (accuracy), :224 (autodiff)."""
 from __future__ import annotations
 
 import torch
@@ -13,31 +14,44 @@ class _HeadXentFn(torch.autograd.Function):
     def forward(ctx, h, weights, bias, labels):
         E = ext()
         B = h.shape[0]
-        hc = h.detach().contiguous()
+        hc = h.detach()
         if hc.dtype not in (torch.bfloat16, torch.float32):
             hc = hc.float()
+        if hc.stride(-1) != 1:
+            hc = hc.contiguous()
         w = weights.detach().float().contiguous()
         b = bias.detach().float().contiguous()
         lab = labels.long().contiguous()
-        if w.shape[1] <= 32:
-            logits, dlogits, loss_sum, correct = E.head_xent(hc, w, b, lab)
-        else:
-            logits = torch.addmm(b, hc.float(), w)
-            dlogits, loss_sum, correct = E.xent_rows(logits, lab)
+        logits, dlogits, loss_sum, correct = E.head_fwd(hc, w, b, lab)
         ctx.save_for_backward(hc, w, dlogits)
         ctx.h_dtype = h.dtype
+        ctx.addrs = (weights.data_ptr(), bias.data_ptr())
         loss = (loss_sum / B).squeeze(0)
         ctx.mark_non_differentiable(logits, correct)
         return logits, loss, correct.squeeze(0)
 
     @staticmethod
     def backward(ctx, _dlogits_unused, dloss, _dcorrect_unused):
+        from .cuda_lstm import grad_sink
+        E = ext()
         hc, w, dlogits = ctx.saved_tensors
-        d = dlogits * dloss
-        dh = (d @ w.t()).to(ctx.h_dtype)
-        dw = hc.float().t() @ d
-        db = d.sum(0)
-        return dh, dw, db, None
+        hcc = hc if hc.is_contiguous() else hc.contiguous()
+        sw, sb = grad_sink(ctx.addrs[0]), grad_sink(ctx.addrs[1])
+        dl = dloss.detach().float().reshape(1).contiguous()
+        if sw is not None and sb is not None and sw[1] == sb[1]:
+            dh = E.head_bwd(hcc, w, dlogits, dl, sw[0], sb[0], sw[1])
+            return dh.to(ctx.h_dtype), None, None, None
+        if sw is not None and sb is not None:             # one of the two already holds a gradient: bring both to "accumulate"
+            if not sw[1]:
+                sw[0].zero_()
+            if not sb[1]:
+                sb[0].zero_()
+            dh = E.head_bwd(hcc, w, dlogits, dl, sw[0], sb[0], True)
+            return dh.to(ctx.h_dtype), None, None, None
+        dw = torch.empty_like(w)
+        db = torch.empty(w.shape[1], dtype=torch.float32, device=w.device)
+        dh = E.head_bwd(hcc, w, dlogits, dl, dw, db, False)
+        return dh.to(ctx.h_dtype), dw, db, None
 
 
 def head_xent(h, weights, bias, labels):

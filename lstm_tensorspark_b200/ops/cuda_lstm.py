@@ -14,6 +14,7 @@ from typing import Optional
 import torch
 
 from .cuda_ext import ext
+from . import cuda_gemm as G
 
 _SYNC_WS = {}
 _SM_COUNT = {}
@@ -28,6 +29,13 @@ USE_TC_GEMM = os.environ.get("LSTM_TS_TC_GEMM", "1") == "1"
 GEMM_VARIANT = int(os.environ.get("LSTM_TS_GEMM_VARIANT", "1"))   # 0: 128x128 tiles, 1: 128x256 tiles (faster on large shapes)
 STATS = {"fast_fwd": 0, "fast_bwd": 0, "generic_fwd": 0, "generic_bwd": 0, "tc_gemm": 0, "kernels": 0}
 
+
+# Gradient-bucket overlap (engine.TrainEngine + parallel/fused_comm.py): LAYER_GRADS_READY is called after a layer's backward
+# has written its weight / bias gradients; callables queued in AFTER_SEQ_BWD are run right after the NEXT persistent backward
+# kernel has been launched (they launch a finished bucket's fused allreduce + update with programmatic dependent launch, so it
+# runs on the SMs that kernel leaves idle).
+HOOKS = {"layer_grads_ready": None}
+AFTER_SEQ_BWD = []
 
 _PARAMS = {}          # fp32 param address -> (bf16 shadow view, fp32 grad view), maintained by models.flat.FlatParams
 DIRECT_GRADS = os.environ.get("LSTM_TS_DIRECT_GRADS", "1") == "1"
@@ -57,17 +65,46 @@ def _lowp(w: torch.Tensor, cd: torch.dtype) -> torch.Tensor:
     return w.detach().to(cd).contiguous()
 
 
-def _accumulate_grad(w_addr: int, a_t: torch.Tensor, b: torch.Tensor):
-    """dW = a_t @ b in fp32.  When the parameter lives in a FlatParams buffer the product is accumulated straight into
-    its grad view (beta = 1 GEMM epilogue, no separate AccumulateGrad add) and None is returned to autograd."""
+def grad_sink(w_addr: int):
+    """-> (fp32 grad view inside the flat buffer, accumulate flag) for a registered parameter, or None.
+    accumulate False = first write of this step: the kernel overwrites (no zero-filled buffer needed)."""
     ent = _lookup(w_addr) if DIRECT_GRADS else None
-    if ent is not None and a_t.dtype == torch.bfloat16:
-        try:
-            torch.addmm(ent[1], a_t, b, out_dtype=torch.float32, out=ent[1])
+    if ent is None:
+        return None
+    owner = ent[2]() if ent[2] is not None else None
+    if owner is None or w_addr not in owner._direct:
+        if owner is not None:
+            owner.ensure_zeroed(w_addr)
+        return ent[1], True
+    return ent[1], owner.take_sink(w_addr)
+
+
+def _accumulate_grad(w_addr: int, a_t: torch.Tensor, b: torch.Tensor):
+    """dW = a_t @ b in fp32 (``a_t`` = dG^T as a transposed view, ``b`` = the layer input: both operands MN-major, read in
+    place by the tcgen05 GEMM).  When the parameter lives in a FlatParams buffer the product lands straight in its grad
+    view (overwrite on the first write of a step, accumulate afterwards) and None is returned to autograd."""
+    sink = grad_sink(w_addr)
+    if sink is not None:
+        G.matmul(a_t, b.t(), out=sink[0], accumulate=sink[1])
+        return None
+    return G.matmul(a_t, b.t(), out_dtype=torch.float32)
+
+
+def _bias_grad(b_addr: int, dg2d: torch.Tensor):
+    """db = column sums of dG; straight into the flat grad view when there is one."""
+    fast = dg2d.is_cuda and dg2d.dtype == torch.bfloat16 and dg2d.shape[1] % 256 == 0 and dg2d.is_contiguous()
+    sink = grad_sink(b_addr)
+    if fast:
+        STATS["kernels"] += 1
+        if sink is not None:
+            ext().colsum_bf16_into(dg2d, sink[0], not sink[1])
             return None
-        except (TypeError, RuntimeError):
-            pass
-    return _mm_f32(a_t, b)
+        return ext().colsum_bf16(dg2d)
+    ones = torch.ones(1, dg2d.shape[0], dtype=dg2d.dtype, device=dg2d.device)
+    if sink is not None:
+        G.matmul(ones, dg2d.t(), out=sink[0].view(1, -1), accumulate=sink[1])
+        return None
+    return G.matmul(ones, dg2d.t(), out_dtype=torch.float32).view(-1)
 
 
 SYNC_WORDS = 8192        # csrc/lstm_seq_tcgen05.cu kSyncWords; the last word is the sticky error flag
@@ -136,29 +173,18 @@ def _batch_chunk(B: int, H: int, dtype: torch.dtype, device) -> Optional[int]:
 
 
 def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    if a.dtype == torch.float32:
-        return a @ b
-    try:
-        return torch.mm(a, b, out_dtype=torch.float32)
-    except (TypeError, RuntimeError):
-        return (a @ b).float()
-
-
-def _transposed(w: torch.Tensor) -> torch.Tensor:
-    """``w [R,C]`` -> contiguous ``[C,R]`` (tile-transpose kernel for 16-bit CUDA tensors)."""
-    if w.is_cuda and w.dim() == 2 and w.element_size() == 2 and w.is_contiguous():
-        STATS["kernels"] += 1
-        return ext().transpose2d(w)
-    return w.t().contiguous()
+    """a [M,K] @ b [K,N] -> fp32 (own kernels: tcgen05 when bf16 and aligned, CUDA-core GEMM otherwise)."""
+    return G.matmul(a, b.t(), out_dtype=torch.float32)
 
 
 def _gemm_tn(a: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
-    """a [M,K] @ w[N,K]^T -> [M,N] in a.dtype; tcgen05 kernel when bf16 and aligned, library GEMM otherwise."""
-    if USE_TC_GEMM and a.dtype == torch.bfloat16 and a.shape[1] % 8 == 0 and w.shape[0] % 8 == 0 and a.shape[0] >= 128:
-        STATS["tc_gemm"] += 1
-        STATS["kernels"] += 1
-        return ext().gemm_bf16_tn(a.contiguous(), w.contiguous(), None, False, GEMM_VARIANT)
-    return a @ w.t()
+    """a [M,K] @ w[N,K]^T -> [M,N] in a.dtype."""
+    STATS["tc_gemm"] += 1
+    STATS["kernels"] += 1
+    return G.matmul(a, w, out_dtype=a.dtype)
+
+
+_CHUNKING = {"on": False}      # True while lstm_layer_sequence feeds batch chunks (weight gradients then accumulate over calls)
 
 
 class _LSTMSeqFn(torch.autograd.Function):
@@ -186,9 +212,10 @@ class _LSTMSeqFn(torch.autograd.Function):
             act = torch.empty(T, B, 4 * H, dtype=cd, device=x_seq.device)
             h_seq[0].copy_(h0c)
             c_seq[0].copy_(c0f)
-            w_h_t = w_h_c.t()
+            pre = torch.empty(B, 4 * H, dtype=cd, device=x_seq.device)
             for t in range(T):
-                pre = torch.addmm(gx[t], h_seq[t], w_h_t)
+                pre.copy_(gx[t])
+                G.matmul(h_seq[t], w_h_c, out=pre, accumulate=True)       # pre = gx[t] + h_{t-1} W_h^T
                 h, c, a = E.lstm_pointwise_fwd(pre, bias_f, c_seq[t])
                 h_seq[t + 1].copy_(h)
                 c_seq[t + 1].copy_(c)
@@ -198,8 +225,9 @@ class _LSTMSeqFn(torch.autograd.Function):
         ctx.save_for_backward(x2d, h_seq, c_seq, act, w_x_c, w_h_c)
         ctx.set_materialize_grads(False)       # an unused output must arrive as None, not as a zero-filled [T,B,H] tensor
         ctx.fast = fast
+        ctx.whole_batch = not _CHUNKING["on"]
         ctx.dims = (T, B, D, H)
-        ctx.w_addrs = (w_x.data_ptr(), w_h.data_ptr())
+        ctx.w_addrs = (w_x.data_ptr(), w_h.data_ptr(), bias.data_ptr())
         ctx.in_dtypes = (h0.dtype, c0.dtype)
         # h_T is its own output (not a slice of the first one taken by the caller): a consumer of the final state only - the
         # classifier on top of the stack - then sends back a [B,H] gradient instead of a zero-filled [T,B,H] one
@@ -223,6 +251,8 @@ class _LSTMSeqFn(torch.autograd.Function):
             dpre, dh0, dc0 = E.lstm_seq_bwd(dh_seq, w_hT, act, c_seq, dhT, dcT, _sync_ws(dev), SEQ_VARIANT)
             STATS["fast_bwd"] += 1
             STATS["kernels"] += 1
+            while AFTER_SEQ_BWD:                 # finished gradient buckets of the layers above: sync them under this recurrence
+                AFTER_SEQ_BWD.pop(0)()
         else:
             dpre = torch.empty_like(act)
             dh_rec: Optional[torch.Tensor] = dhT if dh_T is not None else None
@@ -238,14 +268,13 @@ class _LSTMSeqFn(torch.autograd.Function):
         dg_t = dg2d.t()
         dw_x = _accumulate_grad(ctx.w_addrs[0], dg_t, x2d)
         dw_h = _accumulate_grad(ctx.w_addrs[1], dg_t, h_seq[:T].reshape(T * B, H))
-        if dg2d.is_cuda and dg2d.dtype == torch.bfloat16 and dg2d.shape[1] % 256 == 0 and dg2d.is_contiguous():
-            db = E.colsum_bf16(dg2d)
-            STATS["kernels"] += 1
-        else:
-            db = torch.sum(dg2d, dim=0, dtype=torch.float32)
+        db = _bias_grad(ctx.w_addrs[2], dg2d)
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = _gemm_tn(dg2d, _transposed(w_x_c)).view(T, B, D) if cd == torch.bfloat16 else (dg2d @ w_x_c).view(T, B, D)
+            dx = G.matmul(dg2d, w_x_c.t(), out_dtype=cd).view(T, B, D)        # dG · W_x: W_x read in place as an MN-major operand
+            STATS["kernels"] += 1
+        if HOOKS["layer_grads_ready"] is not None and ctx.whole_batch:
+            HOOKS["layer_grads_ready"]()
         h0_dt, c0_dt = ctx.in_dtypes
         return dx, dh0.to(h0_dt), dc0.to(c0_dt), dw_x, dw_h, db
 
@@ -262,8 +291,12 @@ def lstm_layer_sequence(x_seq, h0, c0, w_x, w_h, bias):
     if chunk is not None:
         # more batch tiles than the persistent kernels can keep co-resident: the sequences are independent, so run the fast
         # path per batch chunk (weight-gradient contributions accumulate across chunks) instead of the per-step generic path
-        outs = [_LSTMSeqFn.apply(x_seq[:, b0:b0 + chunk].contiguous(), h0[b0:b0 + chunk], c0[b0:b0 + chunk], w_x, w_h, bias)
-                for b0 in range(0, B, chunk)]
+        _CHUNKING["on"] = True
+        try:
+            outs = [_LSTMSeqFn.apply(x_seq[:, b0:b0 + chunk].contiguous(), h0[b0:b0 + chunk], c0[b0:b0 + chunk], w_x, w_h, bias)
+                    for b0 in range(0, B, chunk)]
+        finally:
+            _CHUNKING["on"] = False
         STATS["batch_chunks"] = STATS.get("batch_chunks", 0) + len(outs)
         return (torch.cat([o[0] for o in outs], dim=1), torch.cat([o[1] for o in outs], dim=0),
                 torch.cat([o[2] for o in outs], dim=0))

@@ -10,9 +10,9 @@ def flat_step(opt, grad_scale: float = 1.0) -> None:
     shadow = fl.shadow
     if opt.kind == "adam":
         E.flat_adam(fl.data, fl.grad, opt.m, opt.v, shadow, opt.lr, opt.beta1, opt.beta2, opt.eps,
-                    opt.weight_decay, grad_scale, opt.step_dev)
+                    opt.weight_decay, grad_scale, opt.step_dev, opt.wd_numel)
     else:
-        E.flat_sgd(fl.data, fl.grad, shadow, opt.lr, opt.weight_decay, grad_scale)
+        E.flat_sgd(fl.data, fl.grad, shadow, opt.lr, opt.weight_decay, grad_scale, opt.wd_numel)
 
 
 def cast_shadow(fl) -> None:

@@ -24,6 +24,7 @@ class FlatOptimizer:
         self.flat = flat
         self.kind = kind
         self.lr, self.beta1, self.beta2, self.eps, self.weight_decay = lr, beta1, beta2, eps, weight_decay
+        self.wd_numel = -1          # weight decay covers flat elements [0, wd_numel); -1 = all (K12: the LSTM variables only)
         self.step_count = 0
         # device-resident mirror of step_count: the Adam kernels derive the bias correction from it, so a captured
         # CUDA graph of the training step stays exact across replays
@@ -50,11 +51,16 @@ class FlatOptimizer:
             cuda_opt.flat_step(self, grad_scale)
             return
         with torch.no_grad():
-            if self.kind == "adam":
-                ref.adam_step_(fl.data, fl.grad, self.m, self.v, self.step_count, self.lr, self.beta1, self.beta2,
-                               self.eps, self.weight_decay, grad_scale)
-            else:
-                ref.sgd_step_(fl.data, fl.grad, self.lr, self.weight_decay, grad_scale)
+            n = fl.data.numel()
+            cut = n if (self.wd_numel < 0 or not self.weight_decay) else min(self.wd_numel, n)
+            for lo, hi, wd in ((0, cut, self.weight_decay), (cut, n, 0.0)):
+                if hi <= lo:
+                    continue
+                if self.kind == "adam":
+                    ref.adam_step_(fl.data[lo:hi], fl.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], self.step_count, self.lr,
+                                   self.beta1, self.beta2, self.eps, wd, grad_scale)
+                else:
+                    ref.sgd_step_(fl.data[lo:hi], fl.grad[lo:hi], self.lr, wd, grad_scale)
             fl.refresh_shadow()
 
     def bias_corrected_lr(self, step: Optional[int] = None) -> float:

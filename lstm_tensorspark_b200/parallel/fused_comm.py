@@ -83,7 +83,8 @@ class FusedComm(TorchDistComm):
         self.use_multicast = os.environ.get("LSTM_TS_AR_MULTICAST", "auto")
         self.blocks_override = 0          # tuning knob (bench/allreduce_sweep.py)
         self.launches = 0
-        self._sliced_state = False        # True once a two-shot fused Adam step has run (m / v maintained per owned slice)
+        self._state_buckets = []          # (lo, hi, two_shot) buckets of the last fused Adam step: who owns which m / v slice
+        self._gs = None
 
     # ------------------------------------------------------------------------------------------------
     def adopt(self, flat: FlatParams):
@@ -120,7 +121,9 @@ class FusedComm(TorchDistComm):
         return bool(self.arena.mc_base)
 
     def _launch(self, mode: int, off_in: int, n: int, lr: float = 0.0, b1: float = 0.0, b2: float = 0.0, eps: float = 0.0,
-                wd: float = 0.0, m=None, v=None, force: Optional[str] = None, step_dev=None):
+                wd: float = 0.0, m=None, v=None, force: Optional[str] = None, step_dev=None, elem_off: int = 0,
+                wd_numel: int = -1, bump_step: bool = True, pdl: bool = False, blocks: int = 0):
+        """One launch over elements [elem_off, elem_off + n) of the symmetric buffers (a gradient bucket or the whole message)."""
         E = ext()
         A = self.arena
         two_shot = (4 * n >= TWO_SHOT_BYTES) if force is None else (force == "two_shot")
@@ -129,13 +132,22 @@ class FusedComm(TorchDistComm):
             off_in_eff = self.off_stage        # one-shot average stages w first
         else:
             off_in_eff = off_in
-        ptrs = self._ptr_table(off_in_eff)
-        E.fused_allreduce(ptrs, A.mc(off_in_eff) if mc else 0, A.mc(self.off_data) if mc else 0,
-                          A.mc(self.off_shadow) if mc else 0, m, v, self.epochs, self.err, n, self.rank, self.world_size,
-                          mode, two_shot, mc,
-                          self.blocks_override or (AR_BLOCKS_LARGE if 4 * n >= (32 << 20) else AR_BLOCKS), lr, b1, b2, eps, wd,
-                          float(self.timeout_s), step_dev)
+        e4, e2 = 4 * elem_off, 2 * elem_off
+        rows = [[p + e4 for p in A.peers(off_in_eff)], [p + e4 for p in A.peers(self.off_data)],
+                [p + e2 for p in A.peers(self.off_shadow)], A.peers(self.off_flags)]
+        ptrs = torch.tensor(rows, dtype=torch.int64)
+        if m is not None and elem_off:
+            m, v = m[elem_off:elem_off + n], v[elem_off:elem_off + n]
+        elif m is not None and m.numel() != n:
+            m, v = m[:n], v[:n]
+        if wd_numel >= 0:
+            wd_numel = max(0, min(n, wd_numel - elem_off))
+        nblk = blocks or self.blocks_override or (AR_BLOCKS_LARGE if 4 * n >= (32 << 20) else AR_BLOCKS)
+        E.fused_allreduce(ptrs, (A.mc(off_in_eff) + e4) if mc else 0, (A.mc(self.off_data) + e4) if mc else 0,
+                          (A.mc(self.off_shadow) + e2) if mc else 0, m, v, self.epochs, self.err, n, self.rank, self.world_size,
+                          mode, two_shot, mc, nblk, lr, b1, b2, eps, wd, float(self.timeout_s), step_dev, wd_numel, bump_step, pdl)
         self.launches += 1
+        return two_shot
 
     # ------------------------------------------------------------------------------------------------
     def average_params_(self, flat: FlatParams, scope: str = "lstm", force: Optional[str] = None):
@@ -144,37 +156,60 @@ class FusedComm(TorchDistComm):
         self._launch(MODE_AVG, self.off_data, hi, force=force)
 
     def grad_step_(self, flat: FlatParams, optimizer, force: Optional[str] = None):
-        optimizer.step_count += 1
-        n = flat.padded_numel
-        if optimizer.kind == "adam":
-            two_shot = (4 * n >= TWO_SHOT_BYTES) if force is None else (force == "two_shot")
-            self._sliced_state = self._sliced_state or two_shot
-            self._launch(MODE_ADAM, self.off_grad, n, optimizer.lr, optimizer.beta1, optimizer.beta2,
-                         optimizer.eps, optimizer.weight_decay, optimizer.m, optimizer.v, force=force,
-                         step_dev=optimizer.step_dev)
-        else:
-            self._launch(MODE_SGD, self.off_grad, n, optimizer.lr, wd=optimizer.weight_decay, force=force)
+        """Whole-message gradient sync + update in one launch (no overlap)."""
+        self.begin_grad_step(flat, optimizer)
+        self.launch_bucket(0, flat.padded_numel, force=force)
 
-    def _owned_slice(self, n: int):
-        """Element range of the flat buffer whose Adam slots THIS rank maintains in the two-shot gradient step
-        (same split as csrc/fused_allreduce.cu: ceil(n4 / world) float4 per rank)."""
-        n4 = n // 4
-        per = (n4 + self.world_size - 1) // self.world_size
-        lo = min(per * self.rank, n4)
-        hi = min(lo + per, n4)
-        return 4 * lo, 4 * hi
+    # -- bucketed gradient sync: a bucket's allreduce + update is launched as soon as its gradients are final ----------
+    def begin_grad_step(self, flat: FlatParams, optimizer):
+        optimizer.step_count += 1
+        self._gs = {"opt": optimizer, "bump": True, "buckets": []}
+        if optimizer.kind == "adam":
+            self._state_buckets = self._gs["buckets"]       # filled as the step's buckets launch; complete between steps
+
+    def launch_bucket(self, lo: int, hi: int, pdl: bool = False, force: Optional[str] = None, blocks: int = 0):
+        gs = self._gs
+        opt = gs["opt"]
+        n = hi - lo
+        if opt.kind == "adam":
+            two = self._launch(MODE_ADAM, self.off_grad, n, opt.lr, opt.beta1, opt.beta2, opt.eps, opt.weight_decay, opt.m, opt.v,
+                               force=force, step_dev=opt.step_dev, elem_off=lo, wd_numel=opt.wd_numel, bump_step=gs["bump"],
+                               pdl=pdl, blocks=blocks)
+        else:
+            two = self._launch(MODE_SGD, self.off_grad, n, opt.lr, wd=opt.weight_decay, force=force, elem_off=lo,
+                               wd_numel=opt.wd_numel, pdl=pdl, blocks=blocks)
+        gs["bump"] = False
+        gs["buckets"].append((lo, hi, bool(two)))
+
+    def _owned_ranges(self):
+        """Element ranges of the flat buffer whose Adam slots THIS rank maintains: a two-shot bucket is split like the kernel
+        splits it (ceil(n4 / world) float4 per rank, csrc/fused_allreduce.cu); a one-shot bucket is updated identically by every
+        rank (rank 0 contributes it)."""
+        out = []
+        for lo, hi, two in self._state_buckets:
+            if not two:
+                if self.rank == 0:
+                    out.append((lo, hi))
+                continue
+            n4 = (hi - lo) // 4
+            per = (n4 + self.world_size - 1) // self.world_size
+            a = min(per * self.rank, n4)
+            b = min(a + per, n4)
+            out.append((lo + 4 * a, lo + 4 * b))
+        return out
 
     def optimizer_state(self, optimizer) -> dict:
-        """The two-shot fused gradient step keeps Adam's (m, v) for 1/N of the elements on each rank (the slice it
-        reduces and updates).  A checkpoint holds the FULL state: every rank contributes exactly its owned slice
-        (everything else masked to zero, whatever it holds) and a sum reassembles it.  Any other mode (parameter
-        averaging: every rank runs its own full optimizer; one-shot: full state everywhere) returns the local state."""
+        """The two-shot fused gradient step keeps Adam's (m, v) for 1/N of every bucket on each rank (the slice it reduces
+        and updates).  A checkpoint holds the FULL state: every rank contributes exactly its owned slices (everything else
+        masked to zero, whatever it holds) and a sum reassembles it.  Any other mode (parameter averaging: every rank runs
+        its own full optimizer) returns the local state."""
         sd = optimizer.state_dict()
-        if self._sliced_state and optimizer.kind == "adam" and self.world_size > 1:
-            lo, hi = self._owned_slice(self.flat.padded_numel)
+        if self._state_buckets and optimizer.kind == "adam" and self.world_size > 1:
             for k in ("m", "v"):
-                full = torch.zeros_like(getattr(optimizer, k))
-                full[lo:hi] = getattr(optimizer, k)[lo:hi]
+                src = getattr(optimizer, k)
+                full = torch.zeros_like(src)
+                for lo, hi in self._owned_ranges():
+                    full[lo:hi] = src[lo:hi]
                 dist.all_reduce(full, op=dist.ReduceOp.SUM)
                 sd[k] = full.cpu()
         return sd

@@ -25,7 +25,7 @@ def test_extension_is_built_and_importable():
     from lstm_tensorspark_b200.ops.cuda_ext import ext
     E = ext()
     assert E.ar_flag_words() == E.ar_max_blocks() * 16
-    for name in ("gemm_bf16_tn", "lstm_seq_fwd", "lstm_seq_bwd", "fused_allreduce", "head_xent", "flat_adam", "lstm_pointwise_fwd"):
+    for name in ("gemm2", "gemm_generic", "lstm_seq_fwd", "lstm_seq_bwd", "fused_allreduce", "head_fwd", "head_bwd", "flat_adam", "lstm_pointwise_fwd"):
         assert hasattr(E._m, name)
 
 
