@@ -10,6 +10,12 @@ framework's models, kernels or engine:
     DistributedDataParallel -> NCCL all_reduce of the gradients every step (bucketed, overlapped)
 
 Same model shape, same schedule (per-step gradient allreduce), same synthetic data shapes as bench.py's own arm.
+
+Two variants, both timed by ``bench.py`` (the better one is the bar):
+  * ``stock``: what the docs tell a user to write - fp32 module, ``torch.autocast(bf16)``, ``batch_first=True``, eager launches;
+  * ``tuned``: what a careful user ends up with - bf16 module weights (no per-step re-cast of 16.8 M weights) with fp32 master
+    copies + fused Adam on the masters, time-major input (no transposes around cuDNN), bf16 gradient buckets in DDP, and the
+    whole step captured in a CUDA graph when there is one rank.
 """
 from __future__ import annotations
 
@@ -21,32 +27,48 @@ import torch.nn.functional as F
 
 
 class CudnnLSTMClassifier(nn.Module):
-    def __init__(self, hidden, in_features, num_classes):
+    def __init__(self, hidden, in_features, num_classes, time_major=False):
         super().__init__()
         assert len(set(hidden)) == 1, "nn.LSTM stacks equal-width layers"
-        self.lstm = nn.LSTM(in_features, hidden[0], num_layers=len(hidden), batch_first=True)
+        self.time_major = time_major
+        self.lstm = nn.LSTM(in_features, hidden[0], num_layers=len(hidden), batch_first=not time_major)
         self.head = nn.Linear(hidden[-1], num_classes)
 
     def forward(self, x):
         out, _ = self.lstm(x)
-        return self.head(out[:, -1, :])
+        return self.head(out[-1] if self.time_major else out[:, -1, :])
 
 
 class BaselineRunner:
-    def __init__(self, hidden, in_features, num_classes, batch, seq_len, rank, world, device, optimizer="adam", lr=1e-3):
+    def __init__(self, hidden, in_features, num_classes, batch, seq_len, rank, world, device, optimizer="adam", lr=1e-3,
+                 variant="stock"):
         self.rank, self.world, self.device = rank, world, device
         self.B, self.T, self.D, self.C = batch, seq_len, in_features, num_classes
+        self.variant = variant
+        self.tuned = variant == "tuned"
+        self.graph = None
         torch.manual_seed(0)
         if world > 1 and not dist.is_initialized():
             dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
-        model = CudnnLSTMClassifier(hidden, in_features, num_classes).to(device)
-        self.model = nn.parallel.DistributedDataParallel(model, device_ids=[device.index]) if world > 1 else model
-        if optimizer == "adam":
-            self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, fused=True)
+        model = CudnnLSTMClassifier(hidden, in_features, num_classes, time_major=self.tuned).to(device)
+        if self.tuned:
+            model = model.to(torch.bfloat16)
+            model.lstm.flatten_parameters()
+        self.model = nn.parallel.DistributedDataParallel(model, device_ids=[device.index], gradient_as_bucket_view=True) if world > 1 else model
+        self.params = [p for p in self.model.parameters()]
+        if self.tuned:                                   # fp32 master weights: the optimizer never sees the bf16 copies
+            self.masters = [p.detach().float().clone().requires_grad_(True) for p in self.params]
+            for m in self.masters:
+                m.grad = torch.zeros_like(m)
+            opt_params = self.masters
         else:
-            self.opt = torch.optim.SGD(self.model.parameters(), lr=lr)
+            opt_params = self.params
+        if optimizer == "adam":
+            self.opt = torch.optim.Adam(opt_params, lr=lr, fused=True, capturable=self.tuned and world == 1)
+        else:
+            self.opt = torch.optim.SGD(opt_params, lr=lr)
 
-    def train_step(self, x, y):
+    def _step_stock(self, x, y):
         self.opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             logits = self.model(x)
@@ -54,6 +76,52 @@ class BaselineRunner:
         loss.backward()
         self.opt.step()
         return loss.detach()
+
+    def _step_tuned(self, x, y):
+        """x arrives batch-major [B,T,D] like in every arm; the time-major view is a stride permutation (cuDNN takes it)."""
+        for p in self.params:
+            p.grad = None
+        logits = self.model(x.transpose(0, 1))
+        loss = F.cross_entropy(logits.float(), y)
+        loss.backward()
+        with torch.no_grad():
+            torch._foreach_copy_([m.grad for m in self.masters], [p.grad for p in self.params])  # bf16 grads -> fp32
+        self.opt.step()
+        with torch.no_grad():
+            torch._foreach_copy_(self.params, self.masters)                                      # fp32 masters -> bf16 weights
+        return loss.detach()
+
+    def train_step(self, x, y):
+        if self.graph is not None:
+            sx, sy, sloss = self.static
+            sx.copy_(x, non_blocking=True)
+            sy.copy_(y, non_blocking=True)
+            self.graph.replay()
+            return sloss
+        return self._step_tuned(x, y) if self.tuned else self._step_stock(x, y)
+
+    def capture(self, x, y, warmup=3):
+        """CUDA-graph the whole step (single rank: NCCL buckets inside a capture are not worth the fragility for a baseline)."""
+        if self.world > 1:
+            return False
+        try:
+            sx, sy = x.clone(), y.clone()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(warmup):
+                    self.train_step(sx, sy)
+            torch.cuda.current_stream().wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                sloss = self.train_step(sx, sy)
+            self.graph, self.static = g, (sx, sy, sloss)
+            return True
+        except Exception as e:                           # noqa: BLE001
+            self.graph = None
+            self.capture_error = repr(e)[:200]
+            torch.cuda.synchronize()
+            return False
 
     def make_steps(self):
         B, T, D, C = self.B, self.T, self.D, self.C
@@ -107,5 +175,9 @@ class BaselineRunner:
             it["k"] = k + 1
             return loss_host
 
+        graphed = False
+        if self.tuned:
+            graphed = self.capture(dev_x[:B], dev_y[:B])
         h2d = B * T * D * 2 + B * 8
-        return step_dev, step_e2e, h2d, 4, 0, {"lstm": "cudnn", "comm": "nccl-ddp" if self.world > 1 else "none"}
+        return step_dev, step_e2e, h2d, 4, 0, {"lstm": "cudnn", "comm": "nccl-ddp" if self.world > 1 else "none",
+                                              "variant": self.variant, "cuda_graph": graphed}

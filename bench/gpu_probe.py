@@ -149,6 +149,42 @@ def check_gemm2():
     _emit("gemm2_dw_check", rel_err=float((gw[:256] - R).abs().max() / R.abs().max()))
 
 
+def check_gemm2_dw():
+    """Why is the NT (both MN-major) weight-gradient product slower than the TN ones?  Isolate operand major, K length, grid."""
+    import torch
+    from lstm_tensorspark_b200.ops.cuda_ext import ext
+    E = ext()
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    TB, H4, D = 32768, 4096, 1024
+    X = (torch.randn(TB, D, device=dev) * 0.5).bfloat16()
+    XT = X.t().contiguous()                      # [D, TB]
+    W = (torch.randn(H4, D, device=dev) * 0.05).bfloat16()
+    WT = W.t().contiguous()                      # [D, 4H]
+    dG = (torch.randn(TB, H4, device=dev) * 0.5).bfloat16()
+    dGT = dG.t().contiguous()                    # [4H, TB]
+    gw = torch.zeros(H4, D, device=dev)
+    fl = 2.0 * TB * H4 * D
+    def t(what, fn):
+        ms = _time_ms(fn)
+        _emit("gemm2_dw", what=what, ms=ms, tflops=fl / ms / 1e9)
+    t("gx TN (A K-major, B K-major)", lambda: E.gemm2(X, W))
+    t("gx with A MN-major (X^T stored)", lambda: E.gemm2(XT, W, a_mn=True))
+    t("gx with B MN-major (W^T stored)", lambda: E.gemm2(X, WT, b_mn=True))
+    t("gx both MN-major", lambda: E.gemm2(XT, WT, a_mn=True, b_mn=True))
+    t("dW NT both MN (dG, X)", lambda: E.gemm2(dG, X, out=gw, a_mn=True, b_mn=True, accumulate=True))
+    t("dW NT overwrite", lambda: E.gemm2(dG, X, out=gw, a_mn=True, b_mn=True, out_fp32=True))
+    t("dW TN on transposed copies (dG^T, X^T K-major)", lambda: E.gemm2(dGT, XT, out=gw, out_fp32=True))
+    t("dW A K-major (dG^T), B MN (X)", lambda: E.gemm2(dGT, X, out=gw, b_mn=True, out_fp32=True))
+    t("dW A MN (dG), B K-major (X^T)", lambda: E.gemm2(dG, XT, out=gw, a_mn=True, out_fp32=True))
+    for mc in (64, 96, 128, 148):
+        t(f"dW NT max_ctas={mc}", lambda: E.gemm2(dG, X, out=gw, a_mn=True, b_mn=True, out_fp32=True, max_ctas=mc))
+    t("dW NT 1-CTA bn256", lambda: E.gemm2(dG, X, out=gw, a_mn=True, b_mn=True, out_fp32=True, ctas=1, bn=256))
+    t("dW NT 2-CTA bn128", lambda: E.gemm2(dG, X, out=gw, a_mn=True, b_mn=True, out_fp32=True, ctas=2, bn=128))
+    for mc in (96, 128):
+        t(f"gx TN max_ctas={mc}", lambda: E.gemm2(X, W, max_ctas=mc))
+
+
 def _seq_case(T, B, H, D, check_bwd=True, time_it=False):
     import torch
     from lstm_tensorspark_b200.ops import cuda_lstm, reference as ref
@@ -383,7 +419,7 @@ def check_iris_gpu():
     _emit("iris_gpu_standalone", rc=r.returncode, tail=(r.stdout + r.stderr)[-600:])
 
 
-CHECKS = {"gemm2": check_gemm2, "seq_h2048": check_seq_h2048, "bwd_tune": check_bwd_tune, "skew": check_skew, "seq_tiles": check_seq_tiles, "seq_tune": check_seq_tune, "env": check_env, "simple": check_simple, "generic": check_generic, "seq_small": check_seq_small,
+CHECKS = {"gemm2": check_gemm2, "gemm2_dw": check_gemm2_dw, "seq_h2048": check_seq_h2048, "bwd_tune": check_bwd_tune, "skew": check_skew, "seq_tiles": check_seq_tiles, "seq_tune": check_seq_tune, "env": check_env, "simple": check_simple, "generic": check_generic, "seq_small": check_seq_small,
           "seq_big": check_seq_big, "engine": check_engine, "iris_gpu": check_iris_gpu}
 
 

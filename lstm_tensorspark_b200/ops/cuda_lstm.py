@@ -177,6 +177,14 @@ def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return G.matmul(a, b.t(), out_dtype=torch.float32)
 
 
+def _transposed(w: torch.Tensor) -> torch.Tensor:
+    """``w [R,C]`` -> contiguous ``[C,R]`` (tile-transpose kernel for 16-bit CUDA tensors)."""
+    if w.is_cuda and w.dim() == 2 and w.element_size() == 2 and w.is_contiguous():
+        STATS["kernels"] += 1
+        return ext().transpose2d(w)
+    return w.t().contiguous()
+
+
 def _gemm_tn(a: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     """a [M,K] @ w[N,K]^T -> [M,N] in a.dtype."""
     STATS["tc_gemm"] += 1
