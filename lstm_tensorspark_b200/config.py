@@ -63,6 +63,8 @@ class Config:
     json_log: str = ""                  # machine readable metrics file
     max_workers: int = 0                # ranks that run concurrently (Spark's local[N]); 0 = min(partitions, visible GPUs) on
                                         # CUDA, = partitions on the CPU.  partitions > workers: a rank trains its partitions in turn
+    deterministic: bool = False         # bit-reproducible runs: the recurrence kernels consume operand blocks in index order (not
+                                        # arrival order), so fp32 accumulation order is fixed (a few % slower)
     grad_buckets: bool = True           # fused comm, grad_allreduce: per-layer buckets synced under the lower layers' backward
     grad_bucket_blocks: int = 32        # CTAs of an overlapped bucket launch (it runs on the SMs the recurrence leaves idle)
     fault_inject: str = ""              # "rank:step" => that rank exits abnormally at that step (test hook)

@@ -19,7 +19,8 @@ int ts_lstm_pointwise_fwd(const void*, const float*, const float*, void*, float*
 int ts_transpose01_rows(const void*, void*, int, int, long long, cudaStream_t);
 int ts_lstm_seq_cluster_probe(int);
 int ts_transpose2d_b16(const void*, void*, int, int, cudaStream_t);
-int ts_colsum_bf16(const void*, float*, int, int, cudaStream_t);
+int ts_colsum_bf16(const void*, float*, void*, int, int, cudaStream_t);
+long long ts_colsum_scratch_bytes(int, int);
 int ts_lstm_pointwise_bwd(const void*, const float*, const float*, const void*, const float*, const float*, void*,
                           float*, int, int, int, cudaStream_t);
 int ts_head_xent(const void*, const float*, const float*, const long long*, float*, float*, float*, int*, int, int, int,
@@ -40,11 +41,11 @@ int ts_head_bwd(const void*, const float*, const float*, const float*, void*, fl
 int ts_gemm_generic(const void*, const void*, void*, const float*, int, int, int, long long, long long, long long, long long, long long,
                     int, int, int, float, cudaStream_t);
 int ts_gemm2(const void*, const void*, void*, const float*, int, int, int, int, int, int, int, int, int, int, int, int, int,
-             const unsigned int*, unsigned int, int, int*, cudaStream_t);
+             const unsigned int*, const int*, unsigned int*, int*, cudaStream_t);
 int ts_lstm_seq_fwd(const void*, const void*, const float*, const void*, const float*, void*, const float*, void*, void*, int,
-                    int, int, unsigned int*, int, cudaStream_t, const void*);
+                    int, int, unsigned int*, int, cudaStream_t, const void*, const unsigned int*, int, int);
 int ts_lstm_seq_bwd(const void*, const void*, const void*, const float*, const void*, float*, float*, void*, void*, int,
-                    int, int, unsigned int*, int, cudaStream_t);
+                    int, int, unsigned int*, int, cudaStream_t, const unsigned int*, int, int);
 const char* ts_last_error();
 }
 
@@ -93,13 +94,23 @@ Tensor transpose2d(const Tensor& x) {
   return out;
 }
 
+// per-device scratch of the deterministic column-sum kernel (slab partials + tickets; the kernel leaves the tickets zero)
+void* colsum_scratch(const Tensor& x) {
+  static std::vector<Tensor> bufs(64);
+  const int dev = x.device().index();
+  const int64_t need = ts_colsum_scratch_bytes((int)x.size(0), (int)x.size(1));
+  if (!bufs[dev].defined() || bufs[dev].numel() < need)
+    bufs[dev] = torch::zeros({need}, torch::TensorOptions().device(x.device()).dtype(torch::kUInt8));
+  return bufs[dev].data_ptr();
+}
+
 // column sums of a contiguous bf16 [rows, cols] matrix -> fp32 [cols]
 Tensor colsum_bf16(const Tensor& x) {
   chk_cuda(x, "x");
   TORCH_CHECK(x.dim() == 2 && x.is_contiguous() && is_bf16(x) && x.size(1) % 256 == 0, "colsum_bf16: contiguous bf16 [rows, cols], cols % 256 == 0");
   c10::cuda::CUDAGuard g(x.device());
   auto out = torch::zeros({x.size(1)}, x.options().dtype(torch::kFloat32));
-  check(ts_colsum_bf16(x.data_ptr(), out.data_ptr<float>(), (int)x.size(0), (int)x.size(1), stream()), "colsum_bf16");
+  check(ts_colsum_bf16(x.data_ptr(), out.data_ptr<float>(), colsum_scratch(x), (int)x.size(0), (int)x.size(1), stream()), "colsum_bf16");
   return out;
 }
 
@@ -110,7 +121,7 @@ void colsum_bf16_into(const Tensor& x, Tensor out, bool zero_first) {
               "colsum_bf16_into: bf16 [rows, cols % 256 == 0] -> fp32 [cols]");
   c10::cuda::CUDAGuard g(x.device());
   if (zero_first) C10_CUDA_CHECK(cudaMemsetAsync(out.data_ptr(), 0, sizeof(float) * out.numel(), stream()));
-  check(ts_colsum_bf16(x.data_ptr(), out.data_ptr<float>(), (int)x.size(0), (int)x.size(1), stream()), "colsum_bf16_into");
+  check(ts_colsum_bf16(x.data_ptr(), out.data_ptr<float>(), colsum_scratch(x), (int)x.size(0), (int)x.size(1), stream()), "colsum_bf16_into");
 }
 
 // ---- generic LSTM cell epilogue -------------------------------------------------------------------------
@@ -266,7 +277,8 @@ void fused_allreduce(const Tensor& ptrs, int64_t mc_in, int64_t mc_param, int64_
 // out: optional preallocated C (fp32 for accumulate = C += A·B, or any mode); out_fp32 selects the dtype of a fresh C.
 Tensor gemm2(const Tensor& A, const Tensor& B, const std::optional<Tensor>& bias, std::optional<Tensor> out, bool a_mn, bool b_mn,
              bool out_fp32, bool accumulate, int64_t ctas, int64_t bn, int64_t max_ctas, const std::optional<Tensor>& gate,
-             int64_t gate_target, int64_t gate_rows, const std::optional<Tensor>& gate_err) {
+             const std::vector<int64_t>& gate_cfg, const std::optional<Tensor>& done, const std::optional<Tensor>& gate_err,
+             int64_t stream_handle) {
   TORCH_CHECK(A.is_cuda() && B.is_cuda(), "gemm2: CUDA tensors");
   TORCH_CHECK(A.scalar_type() == torch::kBFloat16 && B.scalar_type() == torch::kBFloat16, "gemm2: A/B must be bf16");
   TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && A.stride(1) == 1 && B.stride(1) == 1, "gemm2: 2-D operands with unit inner stride");
@@ -285,10 +297,17 @@ Tensor gemm2(const Tensor& A, const Tensor& B, const std::optional<Tensor>& bias
   }
   const int out_mode = accumulate ? 2 : (C.scalar_type() == torch::kFloat32 ? 1 : 0);
   const unsigned int* gp = nullptr;
-  if (gate.has_value()) { TORCH_CHECK(gate->is_cuda() && gate->scalar_type() == torch::kInt32, "gemm2: gate int32 cuda"); gp = (const unsigned int*)gate->data_ptr<int>(); }
+  int gcfg[7] = {0, 0, 0, 0, 1, 0, 0};
+  if (gate.has_value()) {
+    TORCH_CHECK(gate->is_cuda() && gate->scalar_type() == torch::kInt32 && gate_cfg.size() == 7, "gemm2: gate int32 cuda + 7 config ints");
+    gp = (const unsigned int*)gate->data_ptr<int>();
+    for (int i = 0; i < 7; ++i) gcfg[i] = (int)gate_cfg[i];
+  }
+  unsigned int* dp = nullptr;
+  if (done.has_value()) { TORCH_CHECK(done->is_cuda() && done->scalar_type() == torch::kInt32, "gemm2: done int32 cuda"); dp = (unsigned int*)done->data_ptr<int>(); }
   check(ts_gemm2(A.data_ptr(), B.data_ptr(), C.data_ptr(), fptr(bias), M, N, K, (int)A.stride(0), (int)B.stride(0), (int)C.stride(0),
-                 a_mn ? 1 : 0, b_mn ? 1 : 0, out_mode, (int)ctas, (int)bn, A.device().index(), (int)max_ctas, gp, (unsigned int)gate_target,
-                 (int)gate_rows, gate_err.has_value() ? gate_err->data_ptr<int>() : nullptr, stream()), "gemm2");
+                 a_mn ? 1 : 0, b_mn ? 1 : 0, out_mode, (int)ctas, (int)bn, A.device().index(), (int)max_ctas, gp, gcfg, dp,
+                 gate_err.has_value() ? gate_err->data_ptr<int>() : nullptr, stream_handle ? (cudaStream_t)stream_handle : stream()), "gemm2");
   return C;
 }
 
@@ -313,8 +332,11 @@ Tensor gemm_generic(const Tensor& A, const Tensor& B, const std::optional<Tensor
 // ---- persistent tcgen05 LSTM sequence kernels ------------------------------------------------------------------
 // gx [T,B,4H] bf16 (x·Wx^T, no bias), w_h [4H,H] bf16, bias fp32 [4H], h0 bf16 [B,H], c0 fp32 [B,H]
 // -> h_seq [T+1,B,H] bf16 (row 0 = h0), c_seq [T+1,B,H] fp32, act [T,B,4H] bf16
+// in_gate (wavefront): completion counters of the GEMM that is still producing gx while this kernel runs (see SeqParams);
+// extra_signal: one more arrival after the last step, for a gated GEMM that consumes h_seq.
 std::vector<Tensor> lstm_seq_fwd(const Tensor& gx, const Tensor& w_h, const Tensor& bias, const Tensor& h0,
-                                 const Tensor& c0, Tensor sync_ws, int64_t variant, std::optional<Tensor> dbg) {
+                                 const Tensor& c0, Tensor sync_ws, int64_t variant, std::optional<Tensor> dbg,
+                                 std::optional<Tensor> in_gate, int64_t in_gate_tiles_n, bool extra_signal) {
   chk_cuda(gx, "gx"); chk_cuda(w_h, "w_h"); chk_cuda(bias, "bias"); chk_cuda(h0, "h0"); chk_cuda(c0, "c0");
   c10::cuda::CUDAGuard gd(gx.device());
   int T = gx.size(0), B = gx.size(1), H = gx.size(2) / 4;
@@ -328,7 +350,9 @@ std::vector<Tensor> lstm_seq_fwd(const Tensor& gx, const Tensor& w_h, const Tens
   TORCH_CHECK(h0.scalar_type() == torch::kBFloat16 && c0.scalar_type() == torch::kFloat32, "h0 bf16 / c0 fp32");
   check(ts_lstm_seq_fwd(gx.data_ptr(), w_h.data_ptr(), bias.data_ptr<float>(), h_seq.data_ptr(), c_seq.data_ptr<float>(),
                         act.data_ptr(), c0.data_ptr<float>(), dbg.has_value() ? dbg->data_ptr() : nullptr, tiled.data_ptr(), T, B, H,
-                        (unsigned int*)sync_ws.data_ptr<int>(), (int)variant, stream(), h0.data_ptr()), "lstm_seq_fwd");
+                        (unsigned int*)sync_ws.data_ptr<int>(), (int)variant, stream(), h0.data_ptr(),
+                        in_gate.has_value() ? (const unsigned int*)in_gate->data_ptr<int>() : nullptr, (int)in_gate_tiles_n,
+                        extra_signal ? 1 : 0), "lstm_seq_fwd");
   return {h_seq, c_seq, act};
 }
 
@@ -337,7 +361,7 @@ std::vector<Tensor> lstm_seq_fwd(const Tensor& gx, const Tensor& w_h, const Tens
 // -> dpre [T,B,4H] bf16, dh0 fp32 [B,H], dc0 fp32 [B,H]
 std::vector<Tensor> lstm_seq_bwd(const std::optional<Tensor>& dh_seq, const Tensor& w_hT, const Tensor& act, const Tensor& c_seq,
                                  const Tensor& dhT, const Tensor& dcT, Tensor sync_ws, int64_t variant,
-                                 std::optional<Tensor> dbg) {
+                                 std::optional<Tensor> dbg, std::optional<Tensor> in_gate, int64_t in_gate_tiles_n, bool extra_signal) {
   if (dh_seq.has_value()) chk_cuda(*dh_seq, "dh_seq");
   chk_cuda(w_hT, "w_hT"); chk_cuda(act, "act"); chk_cuda(c_seq, "c_seq");
   c10::cuda::CUDAGuard gd(act.device());
@@ -349,8 +373,44 @@ std::vector<Tensor> lstm_seq_bwd(const std::optional<Tensor>& dh_seq, const Tens
   auto tiled = torch::empty({(int64_t)T, tiles_m, 4 * H / 64, 128, 64}, act.options());   // dG images, written by the kernel
   check(ts_lstm_seq_bwd(dh_seq.has_value() ? dh_seq->data_ptr() : nullptr, w_hT.data_ptr(), act.data_ptr(), c_seq.data_ptr<float>(), dpre.data_ptr(),
                         dh0.data_ptr<float>(), dc0.data_ptr<float>(), dbg.has_value() ? dbg->data_ptr() : nullptr, tiled.data_ptr(), T, B, H,
-                        (unsigned int*)sync_ws.data_ptr<int>(), (int)variant, stream()), "lstm_seq_bwd");
+                        (unsigned int*)sync_ws.data_ptr<int>(), (int)variant, stream(),
+                        in_gate.has_value() ? (const unsigned int*)in_gate->data_ptr<int>() : nullptr, (int)in_gate_tiles_n,
+                        extra_signal ? 1 : 0), "lstm_seq_bwd");
   return {dpre, dh0, dc0};
+}
+
+// Wavefront variants: every buffer is preallocated by the caller (on the main stream, BEFORE it forks side streams) and the
+// launch goes to an explicit stream - the caching allocator never sees a side stream.
+void lstm_seq_fwd_into(const Tensor& gx, const Tensor& w_h, const Tensor& bias, const Tensor& h0, const Tensor& c0, Tensor h_seq,
+                       Tensor c_seq, Tensor act, Tensor tiled, Tensor sync_ws, int64_t variant, std::optional<Tensor> in_gate,
+                       int64_t in_gate_tiles_n, bool extra_signal, int64_t stream_handle) {
+  chk_cuda(gx, "gx"); chk_cuda(w_h, "w_h"); chk_cuda(bias, "bias"); chk_cuda(h0, "h0"); chk_cuda(c0, "c0");
+  chk_cuda(h_seq, "h_seq"); chk_cuda(c_seq, "c_seq"); chk_cuda(act, "act"); chk_cuda(tiled, "tiled");
+  c10::cuda::CUDAGuard gd(gx.device());
+  int T = gx.size(0), B = gx.size(1), H = gx.size(2) / 4;
+  TORCH_CHECK(h_seq.numel() == (int64_t)(T + 1) * B * H && c_seq.numel() == h_seq.numel() && act.numel() == gx.numel(), "lstm_seq_fwd_into: buffer sizes");
+  TORCH_CHECK(tiled.numel() == (int64_t)(T + 1) * ((B + 127) / 128) * 128 * H, "lstm_seq_fwd_into: tile-image buffer size");
+  TORCH_CHECK(h0.scalar_type() == torch::kBFloat16 && c0.scalar_type() == torch::kFloat32, "h0 bf16 / c0 fp32");
+  check(ts_lstm_seq_fwd(gx.data_ptr(), w_h.data_ptr(), bias.data_ptr<float>(), h_seq.data_ptr(), c_seq.data_ptr<float>(),
+                        act.data_ptr(), c0.data_ptr<float>(), nullptr, tiled.data_ptr(), T, B, H, (unsigned int*)sync_ws.data_ptr<int>(),
+                        (int)variant, stream_handle ? (cudaStream_t)stream_handle : stream(), h0.data_ptr(),
+                        in_gate.has_value() ? (const unsigned int*)in_gate->data_ptr<int>() : nullptr, (int)in_gate_tiles_n,
+                        extra_signal ? 1 : 0), "lstm_seq_fwd_into");
+}
+
+void lstm_seq_bwd_into(const std::optional<Tensor>& dh_seq, const Tensor& w_hT, const Tensor& act, const Tensor& c_seq, Tensor dpre,
+                       Tensor dh0, Tensor dc0, Tensor tiled, Tensor sync_ws, int64_t variant, std::optional<Tensor> in_gate,
+                       int64_t in_gate_tiles_n, bool extra_signal, int64_t stream_handle) {
+  chk_cuda(w_hT, "w_hT"); chk_cuda(act, "act"); chk_cuda(c_seq, "c_seq"); chk_cuda(dpre, "dpre"); chk_cuda(dh0, "dh0"); chk_cuda(dc0, "dc0");
+  c10::cuda::CUDAGuard gd(act.device());
+  int T = act.size(0), B = act.size(1), H = act.size(2) / 4;
+  TORCH_CHECK(dpre.numel() == act.numel() && tiled.numel() == (int64_t)T * ((B + 127) / 128) * 128 * 4 * H, "lstm_seq_bwd_into: buffer sizes");
+  TORCH_CHECK(dh0.scalar_type() == torch::kFloat32 && dc0.scalar_type() == torch::kFloat32 && dh0.numel() == (int64_t)B * H && dc0.numel() == (int64_t)B * H, "dh0/dc0 fp32 [B,H]");
+  check(ts_lstm_seq_bwd(dh_seq.has_value() ? dh_seq->data_ptr() : nullptr, w_hT.data_ptr(), act.data_ptr(), c_seq.data_ptr<float>(), dpre.data_ptr(),
+                        dh0.data_ptr<float>(), dc0.data_ptr<float>(), nullptr, tiled.data_ptr(), T, B, H, (unsigned int*)sync_ws.data_ptr<int>(),
+                        (int)variant, stream_handle ? (cudaStream_t)stream_handle : stream(),
+                        in_gate.has_value() ? (const unsigned int*)in_gate->data_ptr<int>() : nullptr, (int)in_gate_tiles_n,
+                        extra_signal ? 1 : 0), "lstm_seq_bwd_into");
 }
 
 }  // namespace
@@ -386,10 +446,18 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("out_fp32") = false, py::arg("beta") = 0.0);
   m.def("gemm2", &gemm2, py::arg("A"), py::arg("B"), py::arg("bias") = py::none(), py::arg("out") = py::none(), py::arg("a_mn") = false,
         py::arg("b_mn") = false, py::arg("out_fp32") = false, py::arg("accumulate") = false, py::arg("ctas") = 2, py::arg("bn") = 256,
-        py::arg("max_ctas") = 0, py::arg("gate") = py::none(), py::arg("gate_target") = 0, py::arg("gate_rows") = 0,
-        py::arg("gate_err") = py::none());
+        py::arg("max_ctas") = 0, py::arg("gate") = py::none(), py::arg("gate_cfg") = std::vector<int64_t>{}, py::arg("done") = py::none(),
+        py::arg("gate_err") = py::none(), py::arg("stream") = 0);
   m.def("lstm_seq_fwd", &lstm_seq_fwd, py::arg("gx"), py::arg("w_h"), py::arg("bias"), py::arg("h0"), py::arg("c0"),
-        py::arg("sync_ws"), py::arg("cluster") = 0, py::arg("dbg") = py::none());
+        py::arg("sync_ws"), py::arg("variant") = 0, py::arg("dbg") = py::none(), py::arg("in_gate") = py::none(),
+        py::arg("in_gate_tiles_n") = 0, py::arg("extra_signal") = false);
+  m.def("lstm_seq_fwd_into", &lstm_seq_fwd_into, py::arg("gx"), py::arg("w_h"), py::arg("bias"), py::arg("h0"), py::arg("c0"),
+        py::arg("h_seq"), py::arg("c_seq"), py::arg("act"), py::arg("tiled"), py::arg("sync_ws"), py::arg("variant"),
+        py::arg("in_gate") = py::none(), py::arg("in_gate_tiles_n") = 0, py::arg("extra_signal") = false, py::arg("stream") = 0);
+  m.def("lstm_seq_bwd_into", &lstm_seq_bwd_into, py::arg("dh_seq"), py::arg("w_hT"), py::arg("act"), py::arg("c_seq"), py::arg("dpre"),
+        py::arg("dh0"), py::arg("dc0"), py::arg("tiled"), py::arg("sync_ws"), py::arg("variant"), py::arg("in_gate") = py::none(),
+        py::arg("in_gate_tiles_n") = 0, py::arg("extra_signal") = false, py::arg("stream") = 0);
   m.def("lstm_seq_bwd", &lstm_seq_bwd, py::arg("dh_seq"), py::arg("w_hT"), py::arg("act"), py::arg("c_seq"), py::arg("dhT"),
-        py::arg("dcT"), py::arg("sync_ws"), py::arg("variant") = 0, py::arg("dbg") = py::none());
+        py::arg("dcT"), py::arg("sync_ws"), py::arg("variant") = 0, py::arg("dbg") = py::none(), py::arg("in_gate") = py::none(),
+        py::arg("in_gate_tiles_n") = 0, py::arg("extra_signal") = false);
 }

@@ -91,11 +91,6 @@ TC_DEVICE void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
 TC_DEVICE void mbar_arrive_cluster(uint32_t cluster_bar_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
-TC_DEVICE unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 // MN-major operand tile: 64-element (128 B) atoms along M/N, 8 KB apart (one TMA box each); 8-row k groups 1024 B apart.
 TC_DEVICE uint64_t desc_mnmajor_sw128(uint32_t smem_addr) { return tc::make_smem_desc(smem_addr, 8192, 1024, tc::LAYOUT_SW128); }
 
@@ -103,11 +98,16 @@ struct Gemm2Params {
   void* C;
   const float* bias;
   int M, N, K, ldc;
-  const unsigned int* gate;      // optional: per-row-group arrival counters
-  unsigned int gate_target;
-  int gate_rows;                 // rows of A covered by one counter
+  // Dataflow gate (layer wavefront): the rows of A are written by a persistent LSTM kernel that is still running.  Rows
+  // [t * gate_rows_per_step, +gate_rows_per_step) belong to time step t; a tile may be loaded once ALL gate_count arrival
+  // counters gate[i * gate_stride] have reached gate_base + gate_per_step * t, with t the last (gate_use_last) or first time
+  // step the tile touches.  done[(tile_m * tiles_n + tile_n) * kCtas + cta]++ publishes a finished 128-row output block.
+  const unsigned int* gate;
+  int gate_count, gate_stride, gate_base, gate_per_step, gate_rows_per_step, gate_use_last;
   long long gate_spin_limit;     // clock64 ticks before giving up (sets *gate_err)
   int* gate_err;
+  unsigned int* done;
+  int reverse_m;                 // walk the M tiles from the last to the first (the backward recurrence runs backwards in time)
 };
 
 template <int kCtas, int BN, bool kAMN, bool kBMN, int kOut>
@@ -135,6 +135,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (p.K + BK - 1) / BK;
   const int cluster_id = blockIdx.x / kCtas, num_clusters = gridDim.x / kCtas;
+  auto tile_m_of = [&](int tile) { const int tm = tile / tiles_n; return p.reverse_m ? tiles_m - 1 - tm : tm; };
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmap_a);
@@ -162,23 +163,32 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     const uint32_t sa0 = tc::smem_u32(smem_a), sb0 = tc::smem_u32(smem_b);
     uint32_t stage = 0, phase = 0;
     bool ok = true;
+    int gate_t_ok = -1;
+    bool gate_dead = false;
     for (int tile = cluster_id; tile < num_tiles && ok; tile += num_clusters) {
-      const int m0 = (tile / tiles_n) * TM + (int)crank * BM;
+      const int m0 = tile_m_of(tile) * TM + (int)crank * BM;
       const int n0 = (tile % tiles_n) * BN + (int)crank * C::kBNCta;
       if (p.gate != nullptr) {
-        // rows [tile_m0, tile_m0 + TM) of A come from a kernel that is still running: wait for their arrival counters
-        const int g0 = ((tile / tiles_n) * TM) / p.gate_rows;
-        const int last_row = min((tile / tiles_n) * TM + TM, p.M) - 1;
-        const int g1 = last_row / p.gate_rows;
-        const long long t0 = clock64();
-        for (int g = g0 + lane; g <= g1; g += 32) {
-          while ((int)(ld_acquire_gpu_u32(p.gate + g) - p.gate_target) < 0) {
-            if (clock64() - t0 > p.gate_spin_limit) { if (p.gate_err) atomicExch(p.gate_err, 1); ok = false; break; }
+        const int r0 = tile_m_of(tile) * TM, r1 = min(r0 + TM, p.M) - 1;
+        const int t = (p.gate_use_last ? r1 : r0) / p.gate_rows_per_step;
+        if (t != gate_t_ok && !gate_dead) {                    // tiles arrive in time order: poll once per time step and CTA
+          const int target = p.gate_base + p.gate_per_step * t;
+          const long long t0 = clock64();
+          for (int g = lane; g < p.gate_count; g += 32) {
+            const unsigned int* c = p.gate + (size_t)g * p.gate_stride;
+            unsigned int v;
+            while (true) {
+              asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+              if ((int)v - target >= 0) break;
+              if (clock64() - t0 > p.gate_spin_limit) { if (p.gate_err) atomicExch(p.gate_err, 1); ok = false; break; }
+            }
           }
+          ok = __all_sync(0xffffffffu, ok);
+          asm volatile("fence.acq_rel.gpu;" ::: "memory");          // the producers' release -> our (TMA) reads
+          asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy observation before async-proxy (TMA) reads
+          if (!ok) { gate_dead = true; ok = true; }                 // producer died: error flag is set, finish the grid without gating
+          gate_t_ok = t;
         }
-        ok = __all_sync(0xffffffffu, ok);
-        asm volatile("fence.proxy.async.global;" ::: "memory");      // generic-proxy observation before async-proxy (TMA) reads
-        if (!ok) break;
       }
       for (int kb = 0, k0 = 0; kb < num_kb; ++kb, k0 += BK) {
         const uint32_t eb = empty0 + 8 * stage, fb = full0 + 8 * stage, fbl = full0_leader + 8 * stage;
@@ -264,7 +274,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     int acc = 0; uint32_t acc_phase = 0;
     const int N = p.N, M = p.M;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m0 = (tile / tiles_n) * TM + (int)crank * BM, n0 = (tile % tiles_n) * BN;
+      const int m0 = tile_m_of(tile) * TM + (int)crank * BM, n0 = (tile % tiles_n) * BN;
       tc::mbar_wait(&tmem_full[acc], acc_phase);
       tc::fence_after_sync();
       const int row = m0 + ew * 32 + lane;
@@ -327,6 +337,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       if (lane == 0) {
         if (kCtas == 2) mbar_arrive_cluster(tempty_leader + 8 * acc);   // the leader's issuer may overwrite this accumulator stage
         else tc::mbar_arrive(&tmem_empty[acc]);
+      }
+      if (p.done != nullptr) {                     // publish this CTA's 128 x BN output block to the gated consumer kernel
+        asm volatile("bar.sync 1, 128;" ::: "memory");           // all four epilogue warps have issued their stores
+        if (ew == 0 && lane == 0)
+          asm volatile("red.release.gpu.global.add.u32 [%0], 1;"
+                       ::"l"(p.done + ((size_t)tile_m_of(tile) * tiles_n + (tile % tiles_n)) * kCtas + crank) : "memory");
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -395,15 +411,19 @@ int launch_major(const void* A, const void* B, const Gemm2Params& p, int lda, in
 
 // A: K-major [M, K] (lda = row pitch) or MN-major [K, M];  B: K-major [N, K] or MN-major [K, N];  C [M, N] row pitch ldc.
 // out_mode: 0 bf16, 1 fp32, 2 fp32 accumulate (C += A·B).  ctas: 1 or 2 (cta_group).  bn: 128 or 256.
-// gate / gate_target / gate_rows: optional dataflow gate on the rows of A (see kernel header); max_ctas > 0 caps the grid.
+// gate_cfg[7] = {count, stride (u32 words), base, per_step, rows_per_step, use_last, reverse_m} (see Gemm2Params); max_ctas > 0 caps the grid.
 extern "C" int ts_gemm2(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, int lda, int ldb, int ldc,
                         int a_mn, int b_mn, int out_mode, int ctas, int bn, int dev, int max_ctas, const unsigned int* gate,
-                        unsigned int gate_target, int gate_rows, int* gate_err, cudaStream_t st) {
+                        const int* gate_cfg, unsigned int* done, int* gate_err, cudaStream_t st) {
   if (K % 8 != 0 || lda % 8 != 0 || ldb % 8 != 0) { ts::set_last_error("gemm2: K and the operand pitches must be multiples of 8"); return -2; }
   if ((a_mn && M % 8 != 0) || (b_mn && N % 8 != 0) || N % 8 != 0) { ts::set_last_error("gemm2: M (MN-major A) / N must be multiples of 8"); return -2; }
   Gemm2Params p{};
   p.C = C; p.bias = bias; p.M = M; p.N = N; p.K = K; p.ldc = ldc;
-  p.gate = gate; p.gate_target = gate_target; p.gate_rows = gate_rows > 0 ? gate_rows : 1; p.gate_err = gate_err;
+  p.gate = gate; p.gate_err = gate_err; p.done = done;
+  if (gate != nullptr) {
+    p.gate_count = gate_cfg[0]; p.gate_stride = gate_cfg[1]; p.gate_base = gate_cfg[2]; p.gate_per_step = gate_cfg[3];
+    p.gate_rows_per_step = gate_cfg[4] > 0 ? gate_cfg[4] : 1; p.gate_use_last = gate_cfg[5]; p.reverse_m = gate_cfg[6];
+  }
   p.gate_spin_limit = 6000000000LL;
   if (ctas == 2) {
     if (bn == 128) return launch_major<2, 128>(A, B, p, lda, ldb, a_mn, b_mn, out_mode, dev, max_ctas, st);

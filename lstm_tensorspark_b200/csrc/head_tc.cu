@@ -265,7 +265,9 @@ int launch_bwd(const void* h, const float* W, const float* dlogits, const float*
     head_bwd_dw_generic<T><<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>((const T*)h, dlogits, dloss, dW, db, B, H, C, accumulate);
     return (int)cudaGetLastError();
   }
-  const int rows = 32;
+  // one slab (no atomics: deterministic) while the dlogits slab fits in shared memory, 32-row slabs + fp32 atomics beyond
+  const int cp = C <= 8 ? 8 : (C <= 16 ? 16 : 32);
+  const int rows = (size_t)B * cp * sizeof(float) <= 40 * 1024 ? B : 32;
   dim3 grid((H + 127) / 128, (B + rows - 1) / rows);
   if (grid.y > 1 && !accumulate) {
     cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)H * C, st);

@@ -154,10 +154,13 @@ extern "C" int ts_transpose2d_b16(const void* src, void* dst, int R, int C, cuda
 
 // Column sums of a bf16 [rows, cols] matrix into fp32 (bias gradient = sum over T*B of the gate gradients): 16 B loads,
 // 8 fp32 accumulators per thread, warps stride over rows, one shared-memory reduction and one atomicAdd per column per block.
-// out must be zero on entry.  cols % 256 == 0.
+// cols % 256 == 0.  Deterministic: every row slab writes its partial sums to a scratch row, the LAST slab to finish (ticket
+// counter per column block) adds the slabs in fixed order and accumulates the result into out (beta = 1).
 namespace {
-__global__ void colsum_bf16_kernel(const uint4* __restrict__ src, float* __restrict__ out, int rows, int cols, int rows_per_block) {
+__global__ void colsum_bf16_kernel(const uint4* __restrict__ src, float* __restrict__ out, float* __restrict__ partial,
+                                   unsigned int* __restrict__ tickets, int rows, int cols, int rows_per_block) {
   __shared__ float red[8][256];
+  __shared__ unsigned int ticket_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cv = blockIdx.x * 32 + lane;                       // 16 B column-vector index (8 columns)
   const int vec_per_row = cols / 8;
@@ -181,14 +184,35 @@ __global__ void colsum_bf16_kernel(const uint4* __restrict__ src, float* __restr
   float s = 0.f;
 #pragma unroll
   for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-  atomicAdd(out + blockIdx.x * 256 + threadIdx.x, s);
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (gridDim.y == 1) { out[col] += s; return; }
+  partial[(size_t)blockIdx.y * cols + col] = s;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) ticket_s = atomicAdd(tickets + blockIdx.x, 1u);
+  __syncthreads();
+  if (ticket_s != gridDim.y - 1) return;
+  __threadfence();
+  float t = 0.f;
+  for (unsigned int y = 0; y < gridDim.y; ++y) t += __ldcg(partial + (size_t)y * cols + col);     // fixed order
+  out[col] += t;
+  if (threadIdx.x == 0) tickets[blockIdx.x] = 0u;              // ready for the next launch
 }
 }  // namespace
 
-extern "C" int ts_colsum_bf16(const void* src, float* out, int rows, int cols, cudaStream_t st) {
+// scratch: fp32 [slabs * cols] + u32 [cols / 256] tickets (zero before first use; the kernel leaves them zero)
+extern "C" long long ts_colsum_scratch_bytes(int rows, int cols) {
+  const int rows_per_block = 512;
+  const long long slabs = (rows + rows_per_block - 1) / rows_per_block;
+  return slabs * cols * 4 + (cols / 256) * 4;
+}
+
+extern "C" int ts_colsum_bf16(const void* src, float* out, void* scratch, int rows, int cols, cudaStream_t st) {
   if (cols % 256 != 0) return -2;
   const int rows_per_block = 512;
   dim3 grid(cols / 256, (rows + rows_per_block - 1) / rows_per_block);
-  colsum_bf16_kernel<<<grid, 256, 0, st>>>((const uint4*)src, out, rows, cols, rows_per_block);
+  float* partial = (float*)scratch;
+  unsigned int* tickets = (unsigned int*)((char*)scratch + (size_t)grid.y * cols * 4);
+  colsum_bf16_kernel<<<grid, 256, 0, st>>>((const uint4*)src, out, partial, tickets, rows, cols, rows_per_block);
   return (int)cudaGetLastError();
 }

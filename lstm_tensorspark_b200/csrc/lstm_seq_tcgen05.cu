@@ -158,6 +158,33 @@ TC_DEVICE U8 ldg_nc32(const void* p) {
                : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
   return r;
 }
+TC_DEVICE U8 ldg_cg32(const void* p) {          // coherent at L2: the producer is a kernel that is still running
+  U8 r;
+  asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p) : "memory");
+  return r;
+}
+TC_DEVICE uint4 ldg_cg16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+// Wait (one lane polls, the warp follows) until the gated GEMM has published the 128 x 256 block that holds this warp's rows.
+TC_DEVICE bool wait_in_gate(const unsigned int* ctr, int lane, volatile int* abort_flag) {
+  int ok = 1;
+  if (lane == 0) {
+    long long t0 = clock64();
+    int n = 0;
+    while (ld_acquire_gpu(ctr) == 0u) {
+      if ((++n & 63) == 0) {
+        if (*abort_flag) { ok = 0; break; }
+        if (clock64() - t0 > kSpinLimit) { *abort_flag = 1; ok = 0; break; }
+      }
+    }
+  }
+  ok = __shfl_sync(0xffffffffu, ok, 0);
+  return ok != 0;
+}
 TC_DEVICE void stg32(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f, uint32_t g, uint32_t h) {
   asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h) : "memory");
 }
@@ -193,6 +220,12 @@ struct SeqParams {
   int tiles_n;                 // CTAs per batch tile
   int sync_mode;               // 0 = k-block arrival counters (dataflow), 1 = one counter per batch tile (grid barrier), 2 = per-CTA flags
   int poll_acquire;            // experiment: ld.acquire polls instead of relaxed
+  // Layer wavefront (two layers' recurrences co-resident, chained through a dataflow-gated GEMM on the idle SMs):
+  const unsigned int* in_gate; // completion counters of the GEMM that produces gx (fwd) / dh_seq (bwd) tile by tile while this kernel
+                               // runs: [(row / 256) * in_gate_tiles_n + col / 256][(row % 256) / 128]; null = the operand is complete
+  int in_gate_tiles_n;
+  int extra_signal;            // one more arrival on this CTA's k-block counter after the LAST step's bookkeeping stores (a gated
+                               // GEMM consumes h_seq / dpre in the natural layout, which is written after the per-step signal)
 };
 
 // Work decomposition
@@ -556,7 +589,15 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
           const bool valid = row < B;
           // operands that do not depend on the GEMM: issue their loads before waiting on the accumulator
           U8 gxw[2];
-          if (valid) {
+          if (p.in_gate != nullptr) {                 // wavefront: gx[t] is produced while we run (this warp's rows: one 128-row block)
+            const size_t gr = (size_t)t * B + (size_t)mb * BM;
+            ok = wait_in_gate(p.in_gate + ((gr >> 8) * p.in_gate_tiles_n + (n0 >> 8)) * 2 + ((gr >> 7) & 1), lane, abort_flag);
+            if (!ok) break;
+            if (valid) {
+              const __nv_bfloat16* gp = p.gx + ((size_t)t * B + row) * (4 * H) + n0;
+              gxw[0] = ldg_cg32(gp); gxw[1] = ldg_cg32(gp + 16);
+            }
+          } else if (valid) {
             const __nv_bfloat16* gp = p.gx + ((size_t)t * B + row) * (4 * H) + n0;
             gxw[0] = ldg_nc32(gp); gxw[1] = ldg_nc32(gp + 16);
             if (t + 2 < p.T && p.debug_mode != 6) prefetch_l2(gp + (size_t)2 * B * (4 * H));     // the x-projection comes from HBM: pull it into L2 early
@@ -669,6 +710,13 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
         }
         tphase ^= 1;
       }
+      if (p.extra_signal && ok) {                 // the last step's h_seq rows (natural layout) are visible to the gated GEMM
+#pragma unroll
+        for (int tile = 0; tile < kTiles; ++tile) {
+          epi_bar();
+          if (etid == 0) signal_counter(p.sync + kSyncKb + ((size_t)(mb0 + tile) * (H / BK) + (in_mb >> 2)) * 32);
+        }
+      }
     } else {
       // after the reduce-scatter this cluster member owns hidden [64 nb + 16 ks, +16); this thread 8 of them
       const int j0 = nb * 64 + ks * 16 + 8 * half;
@@ -703,10 +751,16 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
           const uint32_t xbar = tc::smem_u32(&ss->xchg_full[tile]);
           U8 avw[2], cpv, cnv;
           uint4 dhv;
+          if (p.in_gate != nullptr && s < p.T) {      // wavefront: dh_seq[t] (= dX of the layer above) is produced while we run
+            const size_t gr = (size_t)t * B + (size_t)mb * BM;
+            ok = wait_in_gate(p.in_gate + ((gr >> 8) * p.in_gate_tiles_n + (j0 >> 8)) * 2 + ((gr >> 7) & 1), lane, abort_flag);
+            if (!ok) break;
+          }
           if (valid && s < p.T) {
             const __nv_bfloat16* ap = p.act + ((size_t)t * B + row) * (4 * H) + 4 * j0;
             avw[0] = ldg_nc32(ap); avw[1] = ldg_nc32(ap + 16);
-            dhv = p.dh_seq ? ldg_nc16(p.dh_seq + ((size_t)t * B + row) * H + j0) : make_uint4(0u, 0u, 0u, 0u);
+            dhv = p.dh_seq ? (p.in_gate ? ldg_cg16(p.dh_seq + ((size_t)t * B + row) * H + j0) : ldg_nc16(p.dh_seq + ((size_t)t * B + row) * H + j0))
+                           : make_uint4(0u, 0u, 0u, 0u);
             const float* c0p = p.c_seq + ((size_t)t * B + row) * H + j0;
             const float* c1p = p.c_seq + ((size_t)(t + 1) * B + row) * H + j0;
             cpv = ldg_nc32(c0p);
@@ -715,7 +769,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
             if (t >= 2) {                                                      // saved activations come from HBM: pull t-2 into L2 early
               prefetch_l2(ap - (size_t)2 * B * (4 * H));
               prefetch_l2(c0p - (size_t)2 * B * H);
-              if (p.dh_seq) prefetch_l2(p.dh_seq + ((size_t)(t - 2) * B + row) * H + j0);
+              if (p.dh_seq && !p.in_gate) prefetch_l2(p.dh_seq + ((size_t)(t - 2) * B + row) * H + j0);
             }
           }
           if (s > 0) {
@@ -765,6 +819,10 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
                 *reinterpret_cast<float4*>(p.dh0 + (size_t)row * H + j0 + 4 * i) = make_float4(dh[tile][4 * i], dh[tile][4 * i + 1], dh[tile][4 * i + 2], dh[tile][4 * i + 3]);
                 *reinterpret_cast<float4*>(p.dc0 + (size_t)row * H + j0 + 4 * i) = make_float4(dc[tile][4 * i], dc[tile][4 * i + 1], dc[tile][4 * i + 2], dc[tile][4 * i + 3]);
               }
+            }
+            if (p.extra_signal) {                   // dpre[0] (natural layout, written after the last per-step signal) is visible to the gated GEMM
+              epi_bar();
+              if (etid == 0) signal_counter(p.sync + kSyncKb + ((size_t)mb * (4 * H / BK) + in_mb) * 32);
             }
             continue;
           }
@@ -985,7 +1043,7 @@ static int seq_common(SeqParams& p, const void* w_base, int variant, cudaStream_
 
 extern "C" int ts_lstm_seq_fwd(const void* gx, const void* w_h, const float* bias, const void* h_seq, const float* c_seq,
                                void* act, const float* c0, void* dbg, void* a_tiled, int T, int B, int H, unsigned int* sync_ws, int variant,
-                               cudaStream_t st, const void* h0) {
+                               cudaStream_t st, const void* h0, const unsigned int* in_gate, int in_gate_tiles_n, int extra_signal) {
   {
     const int tiles_m = (B + BM - 1) / BM;
     const int total = tiles_m * BM * (H / 8);
@@ -998,17 +1056,19 @@ extern "C" int ts_lstm_seq_fwd(const void* gx, const void* w_h, const float* bia
   p.a_tiled = (__nv_bfloat16*)a_tiled;
   p.gx = (const __nv_bfloat16*)gx; p.bias = bias; p.h_seq = (__nv_bfloat16*)h_seq; p.c_seq = (float*)c_seq;
   p.act = (__nv_bfloat16*)act; p.sync = sync_ws; p.T = T; p.B = B; p.H = H; p.dbg = (unsigned long long*)dbg;
+  p.in_gate = in_gate; p.in_gate_tiles_n = in_gate_tiles_n; p.extra_signal = extra_signal;
   return seq_common<false>(p, w_h, variant, st);
 }
 
 extern "C" int ts_lstm_seq_bwd(const void* dh_seq, const void* w_hT, const void* act, const float* c_seq, const void* dpre,
                                float* dh0, float* dc0, void* dbg, void* a_tiled, int T, int B, int H, unsigned int* sync_ws, int variant,
-                               cudaStream_t st) {
+                               cudaStream_t st, const unsigned int* in_gate, int in_gate_tiles_n, int extra_signal) {
   cudaMemsetAsync(sync_ws, 0, kSyncErr * sizeof(unsigned int), st);      // arrival counters restart at 0 every launch
   SeqParams p{};
   p.a_tiled = (__nv_bfloat16*)a_tiled;
   p.dh_seq = (const __nv_bfloat16*)dh_seq; p.act = (__nv_bfloat16*)act; p.c_seq = (float*)c_seq; p.dpre = (__nv_bfloat16*)dpre;
   p.dh0 = dh0; p.dc0 = dc0; p.sync = sync_ws; p.T = T; p.B = B; p.H = H; p.dbg = (unsigned long long*)dbg;
+  p.in_gate = in_gate; p.in_gate_tiles_n = in_gate_tiles_n; p.extra_signal = extra_signal;
   return seq_common<true>(p, w_hT, variant, st);
 }
 

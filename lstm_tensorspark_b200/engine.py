@@ -38,6 +38,9 @@ class TrainEngine:
             dtype = torch.bfloat16 if (device.type == "cuda" and cfg.dtype in ("auto", "bf16", "bfloat16")) else torch.float32
         self.dtype = dtype
         F.set_backend(cfg.backend)
+        if cfg.deterministic and device.type == "cuda":
+            from .ops import cuda_lstm
+            cuda_lstm.SEQ_VARIANT = (cuda_lstm.SEQ_VARIANT & ~(7 << 12)) | (3 << 12)     # in-order operand stream
         clear_weight_decay_collection()
         seed = cfg.seed + (1000003 * (rank + 1) if cfg.independent_init else 0)
         gen = torch.Generator(device="cpu")

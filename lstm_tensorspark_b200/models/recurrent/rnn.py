@@ -51,16 +51,34 @@ class RNN(nn.Module):
             return state
         if input_data.dim() != 3:
             raise ValueError(f"expected [B,D] or [B,T,D], got {tuple(input_data.shape)}")
-        seq = input_data.transpose(0, 1)            # time-major [T,B,D]; the kernels index (t, b)
-        for layer in self.layers:
-            seq = layer.fit_sequence(seq)
+        self._run_stack(input_data.transpose(0, 1))  # time-major [T,B,D]; the kernels index (t, b)
         return self.layers[-1].ht                   # = seq[-1], as a separate autograd edge (no [T,B,H] gradient for the top layer)
 
     def fit_sequence_all(self, input_data: torch.Tensor) -> torch.Tensor:
         """``[B,T,D]`` -> last layer's full ``h_seq [T,B,H]``."""
-        seq = input_data.transpose(0, 1)
-        for layer in self.layers:
-            seq = layer.fit_sequence(seq)
+        return self._run_stack(input_data.transpose(0, 1))
+
+    def _run_stack(self, seq: torch.Tensor) -> torch.Tensor:
+        """Layers bottom-up; adjacent pairs run as ONE layer-wavefront op where the GPU path supports it (both recurrences
+        co-resident, the upper layer trailing by a couple of time steps), single layers otherwise."""
+        from ...ops import functional as F
+        i, n = 0, len(self.layers)
+        while i < n:
+            la = self.layers[i]
+            if i + 1 < n and F.lstm_pair_supported(seq, la.num_hidden, self.layers[i + 1].num_hidden):
+                lb = self.layers[i + 1]
+                B = seq.shape[1]
+                for l in (la, lb):
+                    if B != l.ht.shape[0]:
+                        l.reset_state(B)
+                seq, hT_a, cT_a, hT_b, cT_b = F.lstm_pair_sequence(seq, (la.ht, la.Ct, la.w_x, la.w_h, la.bias),
+                                                                     (lb.ht, lb.Ct, lb.w_x, lb.w_h, lb.bias))
+                la._set_state(hT_a, cT_a); la.state.append((hT_a, cT_a))
+                lb._set_state(hT_b, cT_b); lb.state.append((hT_b, cT_b))
+                i += 2
+            else:
+                seq = la.fit_sequence(seq)
+                i += 1
         return seq
 
     # --------------------------------------------------------------------------------------------

@@ -122,6 +122,9 @@ def check_kernel_errors(device) -> None:
     ws = _SYNC_WS.get((device.type, device.index))
     if ws is not None and int(ws[SYNC_WORDS - 1].item()) != 0:
         raise RuntimeError("lstm_seq kernel aborted: an in-kernel wait timed out (see csrc/lstm_seq_tcgen05.cu)")
+    for (di, _tag), ent in list(globals().get("_WS_PAIR", {}).items()):
+        if di == device.index and (int(ent[SYNC_WORDS - 1].item()) != 0 or int(ent[2 * SYNC_WORDS - 1].item()) != 0):
+            raise RuntimeError("lstm_seq kernel (layer wavefront) aborted: an in-kernel wait timed out")
 
 
 def _sms(device) -> int:
@@ -309,3 +312,164 @@ def lstm_layer_sequence(x_seq, h0, c0, w_x, w_h, bias):
         return (torch.cat([o[0] for o in outs], dim=1), torch.cat([o[1] for o in outs], dim=0),
                 torch.cat([o[2] for o in outs], dim=0))
     return _LSTMSeqFn.apply(x_seq.contiguous(), h0, c0, w_x, w_h, bias)
+
+
+# =====================================================================================================================
+# Layer wavefront: two stacked layers' recurrences run CO-RESIDENT (64 + 64 CTAs, two batch tiles per CTA over the same resident
+# weight slice), chained through a dataflow-gated tcgen05 GEMM on the ~20 SMs they leave idle:
+#     forward :  L_a step t  ->  gx_b[t] = h_a[t] W_xb^T (gated GEMM)  ->  L_b step t
+#     backward:  L_b step t  ->  dh_a[t] = dG_b[t] W_xb  (gated GEMM)  ->  L_a step t
+# The reference stacks layers strictly one after the other (/root/reference/src/models/recurrent/rnn.py:38-42); here layer l+1
+# trails layer l by a couple of time steps and the next layer's input projection leaves the critical path altogether.
+# =====================================================================================================================
+WAVEFRONT = os.environ.get("LSTM_TS_WAVEFRONT", "1") == "1"
+_SIDE_STREAMS = {}
+_WS_PAIR = {}
+
+
+def _side_streams(device):
+    key = device.index
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+    return _SIDE_STREAMS[key]
+
+
+def _pair_ws(device, tag: str, n_done: int):
+    """[sync ws of the head kernel | sync ws of the tail kernel | completion counters of the gated GEMM] in one allocation."""
+    key = (device.index, tag)
+    ent = _WS_PAIR.get(key)
+    if ent is None or ent.numel() < 2 * SYNC_WORDS + n_done:
+        ent = torch.zeros(2 * SYNC_WORDS + max(n_done, 1), dtype=torch.int32, device=device)
+        _WS_PAIR[key] = ent
+    return ent[:SYNC_WORDS], ent[SYNC_WORDS:2 * SYNC_WORDS], ent[2 * SYNC_WORDS:2 * SYNC_WORDS + n_done]
+
+
+def wavefront_supported(x_seq: torch.Tensor, h_a: int, h_b: int) -> bool:
+    """Two co-resident layers need: bf16 fast path, B = 256 (two batch tiles per CTA, one GEMM tile per time step), resident
+    weights (H <= 1024), 256-aligned widths, and 2 * H/16 CTAs + a few GEMM CTAs within the device."""
+    if not (WAVEFRONT and x_seq.is_cuda and x_seq.dtype == torch.bfloat16 and not FORCE_GENERIC and x_seq.dim() == 3):
+        return False
+    T, B, D = x_seq.shape
+    if B != 256 or T < 2 or D % 8 != 0 or (SEQ_VARIANT & 15) > 2:
+        return False
+    for h in (h_a, h_b):
+        if h % 256 != 0 or h > 1024:
+            return False
+    return h_a // 16 + h_b // 16 + 8 <= _coresident_ctas(x_seq.device) + 16 and h_a // 16 + h_b // 16 + 8 <= _sms(x_seq.device)
+
+
+class _LSTMPairFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_seq, h0a, c0a, w_xa, w_ha, b_a, h0b, c0b, w_xb, w_hb, b_b):
+        E = ext()
+        dev = x_seq.device
+        T, B, D = x_seq.shape
+        Ha, Hb = w_ha.shape[1], w_hb.shape[1]
+        cd = x_seq.dtype
+        x2d = x_seq.reshape(T * B, D).contiguous()
+        wxa, wha, wxb, whb = _lowp(w_xa, cd), _lowp(w_ha, cd), _lowp(w_xb, cd), _lowp(w_hb, cd)
+        ba_f, bb_f = b_a.detach().float().contiguous(), b_b.detach().float().contiguous()
+        h0a_c, h0b_c = h0a.detach().to(cd).contiguous(), h0b.detach().to(cd).contiguous()
+        c0a_f, c0b_f = c0a.detach().float().contiguous(), c0b.detach().float().contiguous()
+        gx_a = _gemm_tn(x2d, wxa).view(T, B, 4 * Ha)
+        # every buffer is allocated here, on the main stream, before the fork
+        opt = dict(dtype=cd, device=dev)
+        h_seq_a = torch.empty(T + 1, B, Ha, **opt); c_seq_a = torch.empty(T + 1, B, Ha, dtype=torch.float32, device=dev)
+        act_a = torch.empty(T, B, 4 * Ha, **opt); til_a = torch.empty((T + 1) * 2 * 128 * Ha, **opt)
+        h_seq_b = torch.empty(T + 1, B, Hb, **opt); c_seq_b = torch.empty(T + 1, B, Hb, dtype=torch.float32, device=dev)
+        act_b = torch.empty(T, B, 4 * Hb, **opt); til_b = torch.empty((T + 1) * 2 * 128 * Hb, **opt)
+        gx_b = torch.empty(T, B, 4 * Hb, **opt)
+        tn = 4 * Hb // 256
+        ws_a, ws_b, done = _pair_ws(dev, "fwd", T * tn * 2)
+        ws_a[:SYNC_WORDS - 1].zero_(); ws_b[:SYNC_WORDS - 1].zero_(); done.zero_()
+        var = (SEQ_VARIANT & ~15) | 2                                    # two batch tiles per CTA: 64 CTAs per layer at H = 1024
+        main = torch.cuda.current_stream(dev)
+        s_gemm, s_tail = _side_streams(dev)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        s_gemm.wait_event(ev)
+        s_tail.wait_event(ev)
+        # launch order = dependency order of the chain heads: L_a (nothing to wait for), L_b, then the GEMM on what is left
+        E.lstm_seq_fwd_into(gx_a, wha, ba_f, h0a_c, c0a_f, h_seq_a, c_seq_a, act_a, til_a, ws_a, var, None, 0, True, main.cuda_stream)
+        E.lstm_seq_fwd_into(gx_b, whb, bb_f, h0b_c, c0b_f, h_seq_b, c_seq_b, act_b, til_b, ws_b, var, done, tn, False, s_tail.cuda_stream)
+        free_ctas = max(2, (_sms(dev) - Ha // 16 - Hb // 16) // 2 * 2)
+        E.gemm2(h_seq_a[1:].view(T * B, Ha), wxb, out=gx_b.view(T * B, 4 * Hb), ctas=2, bn=256, max_ctas=free_ctas,
+                gate=ws_a[512:], gate_cfg=[2 * (Ha // 64), 32, 8, 4, B, 1, 0], done=done, gate_err=ws_a[SYNC_WORDS - 1:], stream=s_gemm.cuda_stream)
+        e1, e2 = torch.cuda.Event(), torch.cuda.Event()
+        e1.record(s_gemm); e2.record(s_tail)
+        main.wait_event(e1); main.wait_event(e2)
+        STATS["fast_fwd"] += 2
+        STATS["kernels"] += 3
+        STATS["wavefront_fwd"] = STATS.get("wavefront_fwd", 0) + 1
+        ctx.save_for_backward(x2d, h_seq_a, c_seq_a, act_a, h_seq_b, c_seq_b, act_b, wxa, wha, wxb, whb)
+        ctx.set_materialize_grads(False)
+        ctx.dims = (T, B, D, Ha, Hb)
+        ctx.addrs = (w_xa.data_ptr(), w_ha.data_ptr(), b_a.data_ptr(), w_xb.data_ptr(), w_hb.data_ptr(), b_b.data_ptr())
+        ctx.in_dtypes = (h0a.dtype, c0a.dtype, h0b.dtype, c0b.dtype)
+        return h_seq_b[1:], h_seq_a[T], c_seq_a[T], h_seq_b[T], c_seq_b[T]
+
+    @staticmethod
+    def backward(ctx, dh_seq_b, dhT_a, dcT_a, dhT_b, dcT_b):
+        E = ext()
+        x2d, h_seq_a, c_seq_a, act_a, h_seq_b, c_seq_b, act_b, wxa, wha, wxb, whb = ctx.saved_tensors
+        T, B, D, Ha, Hb = ctx.dims
+        cd, dev = act_a.dtype, act_a.device
+        if dh_seq_b is not None:
+            dh_seq_b = dh_seq_b.to(cd).contiguous()
+        f32 = dict(dtype=torch.float32, device=dev)
+        z = lambda g, H: g.float().contiguous().clone() if g is not None else torch.zeros(B, H, **f32)
+        dh0a, dc0a, dh0b, dc0b = z(dhT_a, Ha), z(dcT_a, Ha), z(dhT_b, Hb), z(dcT_b, Hb)
+        whT_a, whT_b = _transposed(wha), _transposed(whb)
+        dpre_a = torch.empty_like(act_a); dpre_b = torch.empty_like(act_b)
+        til_a = torch.empty(T * 2 * 128 * 4 * Ha, dtype=cd, device=dev); til_b = torch.empty(T * 2 * 128 * 4 * Hb, dtype=cd, device=dev)
+        dx_b = torch.empty(T, B, Ha, dtype=cd, device=dev)                # = the gradient into every h_a[t]
+        tn = Ha // 256
+        ws_b, ws_a, done = _pair_ws(dev, "bwd", T * tn * 2)               # head of the backward chain is layer b
+        ws_a[:SYNC_WORDS - 1].zero_(); ws_b[:SYNC_WORDS - 1].zero_(); done.zero_()
+        var = (SEQ_VARIANT & ~15) | 2
+        main = torch.cuda.current_stream(dev)
+        s_gemm, s_tail = _side_streams(dev)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        s_gemm.wait_event(ev)
+        s_tail.wait_event(ev)
+        E.lstm_seq_bwd_into(dh_seq_b, whT_b, act_b, c_seq_b, dpre_b, dh0b, dc0b, til_b, ws_b, var, None, 0, True, main.cuda_stream)
+        E.lstm_seq_bwd_into(dx_b, whT_a, act_a, c_seq_a, dpre_a, dh0a, dc0a, til_a, ws_a, var, done, tn, False, s_tail.cuda_stream)
+        free_ctas = max(2, (_sms(dev) - Ha // 16 - Hb // 16) // 2 * 2)
+        E.gemm2(dpre_b.view(T * B, 4 * Hb), wxb, out=dx_b.view(T * B, Ha), b_mn=True, ctas=2, bn=256, max_ctas=free_ctas,
+                gate=ws_b[512:], gate_cfg=[2 * (4 * Hb // 64), 32, T + 1, -1, B, 0, 1], done=done, gate_err=ws_b[SYNC_WORDS - 1:],
+                stream=s_gemm.cuda_stream)
+        e1, e2 = torch.cuda.Event(), torch.cuda.Event()
+        e1.record(s_gemm); e2.record(s_tail)
+        main.wait_event(e1); main.wait_event(e2)
+        STATS["fast_bwd"] += 2
+        STATS["kernels"] += 5
+        a = ctx.addrs
+        hook = HOOKS["layer_grads_ready"]
+        dg_b = dpre_b.view(T * B, 4 * Hb)
+        dw_xb = _accumulate_grad(a[3], dg_b.t(), h_seq_a[1:].reshape(T * B, Ha))
+        dw_hb = _accumulate_grad(a[4], dg_b.t(), h_seq_b[:T].reshape(T * B, Hb))
+        db_b = _bias_grad(a[5], dg_b)
+        if hook is not None:
+            hook()
+        dg_a = dpre_a.view(T * B, 4 * Ha)
+        dw_xa = _accumulate_grad(a[0], dg_a.t(), x2d)
+        dw_ha = _accumulate_grad(a[1], dg_a.t(), h_seq_a[:T].reshape(T * B, Ha))
+        db_a = _bias_grad(a[2], dg_a)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = G.matmul(dg_a, wxa.t(), out_dtype=cd).view(T, B, D)
+            STATS["kernels"] += 1
+        if hook is not None:
+            hook()
+        t = ctx.in_dtypes
+        return dx, dh0a.to(t[0]), dc0a.to(t[1]), dw_xa, dw_ha, db_a, dh0b.to(t[2]), dc0b.to(t[3]), dw_xb, dw_hb, db_b
+
+
+def lstm_pair_sequence(x_seq, la, lb):
+    """Two stacked layers as one wavefront op.  ``la`` / ``lb`` = (h0, c0, w_x, w_h, bias).  -> (h_seq_b, hT_a, cT_a, hT_b, cT_b)."""
+    if (not x_seq.is_contiguous() and not x_seq.requires_grad and x_seq.transpose(0, 1).is_contiguous()
+            and (x_seq.shape[2] * x_seq.element_size()) % 16 == 0):
+        x_seq = ext().transpose01(x_seq.transpose(0, 1))
+        STATS["kernels"] += 1
+    return _LSTMPairFn.apply(x_seq.contiguous(), *la, *lb)

@@ -55,3 +55,16 @@ def head_xent(h, weights, bias, labels):
         from . import cuda_head
         return cuda_head.head_xent(h, weights, bias, labels)
     return ref.head_xent(h, weights, bias, labels)
+
+
+def lstm_pair_supported(x_seq, h_a: int, h_b: int) -> bool:
+    """Can two stacked layers run as one layer-wavefront op (both recurrences co-resident on the GPU)?"""
+    if not x_seq.is_cuda or _BACKEND == "torch":
+        return False
+    from . import cuda_lstm
+    return cuda_lstm.wavefront_supported(x_seq, h_a, h_b)
+
+
+def lstm_pair_sequence(x_seq, la, lb):
+    from . import cuda_lstm
+    return cuda_lstm.lstm_pair_sequence(x_seq, la, lb)

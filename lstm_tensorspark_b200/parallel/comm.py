@@ -80,6 +80,7 @@ class TorchDistComm(Communicator):
     def __init__(self, rank: int, world_size: int, backend: str, device: torch.device, timeout_s: float = 600.0):
         super().__init__(rank, world_size)
         self.name = backend
+        self.backend = backend          # the torch.distributed backend (subclasses may change `name`)
         self.device = device
         if not dist.is_initialized():
             kw = {}
@@ -90,7 +91,7 @@ class TorchDistComm(Communicator):
         self.group = dist.group.WORLD
 
     def barrier(self):
-        if self.name == "nccl":
+        if self.backend == "nccl":
             dist.barrier(device_ids=[self.device.index])
         else:
             dist.barrier()
@@ -106,7 +107,7 @@ class TorchDistComm(Communicator):
         return out
 
     def max_scalar(self, v: float) -> float:
-        t = torch.tensor([v], dtype=torch.float64, device=self.device if self.name == "nccl" else "cpu")
+        t = torch.tensor([v], dtype=torch.float64, device=self.device if self.backend == "nccl" else "cpu")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
@@ -126,7 +127,7 @@ class TorchDistComm(Communicator):
         flat.refresh_shadow()
 
     def allreduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
-        buf = t.to(self.device) if self.name == "nccl" else t.cpu()
+        buf = t.to(self.device) if self.backend == "nccl" else t.cpu()
         dist.all_reduce(buf, op=dist.ReduceOp.SUM)
         t.copy_(buf.to(t.device))
         return t

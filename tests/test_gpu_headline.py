@@ -98,3 +98,41 @@ def test_weight_decay_in_the_update_kernel_matches_autograd_l2():
     total = float(eng.step(x, y))
     assert abs(total - total_expect) < 1e-3 * max(1.0, abs(total_expect))
     assert (eng.flat.data - w_expect).abs().max() < 1e-4
+
+
+def test_layer_wavefront_matches_sequential_layers():
+    """The two-layer wavefront op (both recurrences co-resident, chained through the gated GEMM) against the same two layers run
+    one after the other: forward states and every gradient, full-sequence loss so that dh_seq flows into the top layer too."""
+    from lstm_tensorspark_b200.ops import cuda_lstm
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(11)
+    T, B, D, Ha, Hb = 12, 256, 256, 512, 256
+    mk = lambda *s, sc=1.0: (torch.randn(*s, device=dev) * sc)
+    x = mk(T, B, D, sc=0.5).bfloat16()
+    pa = [mk(B, Ha, sc=0.1), mk(B, Ha, sc=0.1), mk(4 * Ha, D, sc=D ** -0.5), mk(4 * Ha, Ha, sc=Ha ** -0.5), mk(4 * Ha, sc=0.1)]
+    pb = [mk(B, Hb, sc=0.1), mk(B, Hb, sc=0.1), mk(4 * Hb, Ha, sc=Ha ** -0.5), mk(4 * Hb, Hb, sc=Hb ** -0.5), mk(4 * Hb, sc=0.1)]
+    wgt = mk(T, B, Hb)
+
+    def run(pair):
+        xa = x.clone().requires_grad_(True)
+        a = [p.clone().requires_grad_(True) for p in pa]
+        b = [p.clone().requires_grad_(True) for p in pb]
+        if pair:
+            assert cuda_lstm.wavefront_supported(xa, Ha, Hb)
+            hs, hTa, cTa, hTb, cTb = cuda_lstm.lstm_pair_sequence(xa, a, b)
+        else:
+            hs_a, hTa, cTa = cuda_lstm.lstm_layer_sequence(xa, *a)
+            hs, hTb, cTb = cuda_lstm.lstm_layer_sequence(hs_a, *b)
+        loss = (hs.float() * wgt).sum() + hTa.float().sum() + cTa.float().sum() * 0.5 + hTb.float().sum() + cTb.float().sum() * 0.25
+        loss.backward()
+        torch.cuda.synchronize()
+        cuda_lstm.check_kernel_errors(dev)
+        return [hs.detach().float(), hTa.detach().float(), cTa.detach().float(), cTb.detach().float(), xa.grad.float()] + \
+               [p.grad.float() for p in a + b]
+
+    ref = run(False)
+    n0 = cuda_lstm.STATS.get("wavefront_fwd", 0)
+    got = run(True)
+    assert cuda_lstm.STATS.get("wavefront_fwd", 0) == n0 + 1
+    for i, (g, r) in enumerate(zip(got, ref)):
+        assert _rel_l2(g, r) <= 5e-3, (i, tuple(r.shape), _rel_l2(g, r))
