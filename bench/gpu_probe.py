@@ -185,6 +185,124 @@ def check_gemm2_dw():
         t(f"gx TN max_ctas={mc}", lambda: E.gemm2(X, W, max_ctas=mc))
 
 
+def check_wave():
+    """Layer-wavefront bring-up: the three co-resident kernels piece by piece, dumping the dataflow counters after each stage."""
+    import torch
+    from lstm_tensorspark_b200.ops import cuda_lstm as CL
+    from lstm_tensorspark_b200.ops.cuda_ext import ext
+    E = ext()
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    T, B, D, Ha, Hb = 6, 256, 256, 1024, 1024
+    cd = torch.bfloat16
+    x2d = (torch.randn(T * B, D, device=dev) * 0.5).to(cd)
+    wxa = (torch.randn(4 * Ha, D, device=dev) * D ** -0.5).to(cd); wha = (torch.randn(4 * Ha, Ha, device=dev) * Ha ** -0.5).to(cd)
+    wxb = (torch.randn(4 * Hb, Ha, device=dev) * Ha ** -0.5).to(cd); whb = (torch.randn(4 * Hb, Hb, device=dev) * Hb ** -0.5).to(cd)
+    ba = torch.zeros(4 * Ha, device=dev); bb = torch.zeros(4 * Hb, device=dev)
+    h0a = torch.zeros(B, Ha, device=dev, dtype=cd); c0a = torch.zeros(B, Ha, device=dev)
+    h0b = torch.zeros(B, Hb, device=dev, dtype=cd); c0b = torch.zeros(B, Hb, device=dev)
+    gx_a = E.gemm2(x2d, wxa).view(T, B, 4 * Ha)
+    opt = dict(dtype=cd, device=dev)
+    def bufs(H):
+        return (torch.empty(T + 1, B, H, **opt), torch.empty(T + 1, B, H, dtype=torch.float32, device=dev), torch.empty(T, B, 4 * H, **opt),
+                torch.empty((T + 1) * 2 * 128 * H, **opt))
+    tn = 4 * Hb // 256
+    ws_a, ws_b, done = CL._pair_ws(dev, "probe", T * tn * 2)
+    var = 2
+    def ctrs(ws, n):
+        return [int(v) for v in ws[512:512 + 32 * n:32].cpu()]
+    # stage 1: L_a alone, two tiles per CTA, extra signal
+    ws_a.zero_(); ws_b.zero_(); done.zero_()
+    ha, ca, aa, ta = bufs(Ha)
+    E.lstm_seq_fwd_into(gx_a, wha, ba, h0a, c0a, ha, ca, aa, ta, ws_a, var, None, 0, True, 0)
+    torch.cuda.synchronize()
+    ref_h, _, _ = E.lstm_seq_fwd(gx_a, wha, ba, h0a, c0a, CL._sync_ws(dev), 0)
+    torch.cuda.synchronize()
+    _emit("wave_stage1", err=int(ws_a[-1]), counters=ctrs(ws_a, 32)[:6], expect=4 * (T + 1), h_diff=float((ha.float() - ref_h.float()).abs().max()))
+    # stage 2: + gated GEMM on a side stream (L_a re-run so that the GEMM really waits)
+    ws_a.zero_(); done.zero_()
+    gx_b = torch.zeros(T, B, 4 * Hb, **opt)
+    s1 = torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    ev = torch.cuda.Event(); ev.record(main); s1.wait_event(ev)
+    E.lstm_seq_fwd_into(gx_a, wha, ba, h0a, c0a, ha, ca, aa, ta, ws_a, var, None, 0, True, main.cuda_stream)
+    E.gemm2(ha[1:].view(T * B, Ha), wxb, out=gx_b.view(T * B, 4 * Hb), ctas=1, bn=256, max_ctas=20, gate=ws_a[512:],
+            gate_cfg=[2 * (Ha // 64), 32, 8, 4, B, 1, 0], done=done, gate_err=ws_a[-1:], stream=s1.cuda_stream)
+    torch.cuda.synchronize()
+    ref_gx = (ha[1:].reshape(T * B, Ha).float() @ wxb.float().t()).view(T, B, 4 * Hb)
+    _emit("wave_stage2", err=int(ws_a[-1]), done_min=int(done.min()), done_max=int(done.max()), done_n=int(done.numel()),
+          gx_rel=float((gx_b.float() - ref_gx).abs().max() / ref_gx.abs().max()))
+    # stage 3: all three
+    ws_a.zero_(); ws_b.zero_(); done.zero_()
+    hb, cb, ab, tb = bufs(Hb)
+    s2 = torch.cuda.Stream()
+    ev = torch.cuda.Event(); ev.record(main); s1.wait_event(ev); s2.wait_event(ev)
+    E.lstm_seq_fwd_into(gx_a, wha, ba, h0a, c0a, ha, ca, aa, ta, ws_a, var, None, 0, True, main.cuda_stream)
+    E.lstm_seq_fwd_into(gx_b, whb, bb, h0b, c0b, hb, cb, ab, tb, ws_b, var, done, tn, False, s2.cuda_stream)
+    E.gemm2(ha[1:].view(T * B, Ha), wxb, out=gx_b.view(T * B, 4 * Hb), ctas=1, bn=256, max_ctas=20, gate=ws_a[512:],
+            gate_cfg=[2 * (Ha // 64), 32, 8, 4, B, 1, 0], done=done, gate_err=ws_a[-1:], stream=s1.cuda_stream)
+    try:
+        torch.cuda.synchronize()
+        ref_hb, _, _ = E.lstm_seq_fwd(ref_gx.to(cd), whb, bb, h0b, c0b, CL._sync_ws(dev), 0)
+        torch.cuda.synchronize()
+        _emit("wave_stage3", err_a=int(ws_a[-1]), err_b=int(ws_b[-1]), a_ctr=ctrs(ws_a, 32)[:4], b_ctr=ctrs(ws_b, 32)[:4],
+              done_min=int(done.min()), done_max=int(done.max()), hb_diff=float((hb.float() - ref_hb.float()).abs().max()))
+    except Exception as e:           # noqa: BLE001
+        _emit("wave_stage3_EXC", error=repr(e)[:300])
+        raise
+
+
+def check_wave_bwd():
+    """Backward half of the wavefront through the autograd op; dumps the dataflow counters of all three kernels afterwards."""
+    import torch
+    from lstm_tensorspark_b200.ops import cuda_lstm as CL
+    dev = torch.device("cuda")
+    torch.manual_seed(11)
+    import os
+    last_only = os.environ.get("LAST_ONLY", "0") == "1"
+    for (T, Ha, Hb, D) in ((6, 1024, 1024, 256), (128, 1024, 1024, 1024)):
+        B = 256
+        mk = lambda *s, sc=1.0: (torch.randn(*s, device=dev) * sc)
+        x = mk(T, B, D, sc=0.5).bfloat16()
+        pa = [mk(B, Ha, sc=0.1), mk(B, Ha, sc=0.1), mk(4 * Ha, D, sc=D ** -0.5), mk(4 * Ha, Ha, sc=Ha ** -0.5), mk(4 * Ha, sc=0.1)]
+        pb = [mk(B, Hb, sc=0.1), mk(B, Hb, sc=0.1), mk(4 * Hb, Ha, sc=Ha ** -0.5), mk(4 * Hb, Hb, sc=Hb ** -0.5), mk(4 * Hb, sc=0.1)]
+        wgt = mk(T, B, Hb)
+        def run(pair):
+            xa = x.clone().requires_grad_(True)
+            a = [p.clone().requires_grad_(True) for p in pa]
+            b = [p.clone().requires_grad_(True) for p in pb]
+            if pair:
+                hs, hTa, cTa, hTb, cTb = CL.lstm_pair_sequence(xa, a, b)
+            else:
+                hs_a, hTa, cTa = CL.lstm_layer_sequence(xa, *a)
+                hs, hTb, cTb = CL.lstm_layer_sequence(hs_a, *b)
+            loss = hTb.float().sum() if last_only else (hs.float() * wgt).sum() + hTa.float().sum() + hTb.float().sum()
+            torch.cuda.synchronize()
+            t0 = time.time()
+            loss.backward()
+            torch.cuda.synchronize()
+            return [hs.detach().float(), xa.grad.float()] + [p.grad.float() for p in a + b if p.grad is not None], time.time() - t0
+        ref, _ = run(False)
+        try:
+            got, dt = run(True)
+        except Exception as e:       # noqa: BLE001
+            got, dt = None, -1.0
+            _emit("wave_bwd_EXC", T=T, error=repr(e)[:200])
+        def c(tag, i, n):
+            ent = CL._WS_PAIR.get((0, tag))
+            if ent is None:
+                return None
+            ws = ent[i * 8192:(i + 1) * 8192]
+            return {"err": int(ws[-1]), "ctr": [int(v) for v in ws[512:512 + 32 * n:32].cpu()][:5]}
+        ent = CL._WS_PAIR.get((0, "bwd"))
+        dn = ent[2 * 8192:2 * 8192 + T * (Ha // 256) * 2] if ent is not None else None
+        rel = None
+        if got is not None:
+            rel = [float((g - r).norm() / (r.norm() + 1e-30)) for g, r in zip(got, ref)]
+        _emit("wave_bwd", T=T, seconds=dt, head_b=c("bwd", 0, 128), tail_a=c("bwd", 1, 128), fwd_a=c("fwd", 0, 32), fwd_b=c("fwd", 1, 32),
+              done_min=None if dn is None else int(dn.min()), done_zero=None if dn is None else int((dn == 0).sum()), rel=rel)
+
+
 def _seq_case(T, B, H, D, check_bwd=True, time_it=False):
     import torch
     from lstm_tensorspark_b200.ops import cuda_lstm, reference as ref
@@ -419,7 +537,7 @@ def check_iris_gpu():
     _emit("iris_gpu_standalone", rc=r.returncode, tail=(r.stdout + r.stderr)[-600:])
 
 
-CHECKS = {"gemm2": check_gemm2, "gemm2_dw": check_gemm2_dw, "seq_h2048": check_seq_h2048, "bwd_tune": check_bwd_tune, "skew": check_skew, "seq_tiles": check_seq_tiles, "seq_tune": check_seq_tune, "env": check_env, "simple": check_simple, "generic": check_generic, "seq_small": check_seq_small,
+CHECKS = {"wave": check_wave, "wave_bwd": check_wave_bwd, "gemm2": check_gemm2, "gemm2_dw": check_gemm2_dw, "seq_h2048": check_seq_h2048, "bwd_tune": check_bwd_tune, "skew": check_skew, "seq_tiles": check_seq_tiles, "seq_tune": check_seq_tune, "env": check_env, "simple": check_simple, "generic": check_generic, "seq_small": check_seq_small,
           "seq_big": check_seq_big, "engine": check_engine, "iris_gpu": check_iris_gpu}
 
 

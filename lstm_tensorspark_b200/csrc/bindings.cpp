@@ -41,11 +41,12 @@ int ts_head_bwd(const void*, const float*, const float*, const float*, void*, fl
 int ts_gemm_generic(const void*, const void*, void*, const float*, int, int, int, long long, long long, long long, long long, long long,
                     int, int, int, float, cudaStream_t);
 int ts_gemm2(const void*, const void*, void*, const float*, int, int, int, int, int, int, int, int, int, int, int, int, int,
-             const unsigned int*, const int*, unsigned int*, int*, cudaStream_t);
+             const unsigned int*, const int*, unsigned int*, int*, int, cudaStream_t);
 int ts_lstm_seq_fwd(const void*, const void*, const float*, const void*, const float*, void*, const float*, void*, void*, int,
-                    int, int, unsigned int*, int, cudaStream_t, const void*, const unsigned int*, int, int);
+                    int, int, unsigned int*, int, cudaStream_t, const void*, const unsigned int*, int, int, int);
 int ts_lstm_seq_bwd(const void*, const void*, const void*, const float*, const void*, float*, float*, void*, void*, int,
-                    int, int, unsigned int*, int, cudaStream_t, const unsigned int*, int, int);
+                    int, int, unsigned int*, int, cudaStream_t, const unsigned int*, int, int, int);
+int ts_lstm_seq_prologue(const void*, const float*, void*, float*, void*, unsigned int*, int, int, cudaStream_t);
 const char* ts_last_error();
 }
 
@@ -99,7 +100,7 @@ void* colsum_scratch(const Tensor& x) {
   static std::vector<Tensor> bufs(64);
   const int dev = x.device().index();
   const int64_t need = ts_colsum_scratch_bytes((int)x.size(0), (int)x.size(1));
-  if (!bufs[dev].defined() || bufs[dev].numel() < need)
+  if (!bufs[dev].defined() || bufs[dev].numel() < need)        // (a bigger buffer starts with zeroed tickets again)
     bufs[dev] = torch::zeros({need}, torch::TensorOptions().device(x.device()).dtype(torch::kUInt8));
   return bufs[dev].data_ptr();
 }
@@ -278,7 +279,7 @@ void fused_allreduce(const Tensor& ptrs, int64_t mc_in, int64_t mc_param, int64_
 Tensor gemm2(const Tensor& A, const Tensor& B, const std::optional<Tensor>& bias, std::optional<Tensor> out, bool a_mn, bool b_mn,
              bool out_fp32, bool accumulate, int64_t ctas, int64_t bn, int64_t max_ctas, const std::optional<Tensor>& gate,
              const std::vector<int64_t>& gate_cfg, const std::optional<Tensor>& done, const std::optional<Tensor>& gate_err,
-             int64_t stream_handle) {
+             int64_t stream_handle, bool pdl) {
   TORCH_CHECK(A.is_cuda() && B.is_cuda(), "gemm2: CUDA tensors");
   TORCH_CHECK(A.scalar_type() == torch::kBFloat16 && B.scalar_type() == torch::kBFloat16, "gemm2: A/B must be bf16");
   TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && A.stride(1) == 1 && B.stride(1) == 1, "gemm2: 2-D operands with unit inner stride");
@@ -307,7 +308,8 @@ Tensor gemm2(const Tensor& A, const Tensor& B, const std::optional<Tensor>& bias
   if (done.has_value()) { TORCH_CHECK(done->is_cuda() && done->scalar_type() == torch::kInt32, "gemm2: done int32 cuda"); dp = (unsigned int*)done->data_ptr<int>(); }
   check(ts_gemm2(A.data_ptr(), B.data_ptr(), C.data_ptr(), fptr(bias), M, N, K, (int)A.stride(0), (int)B.stride(0), (int)C.stride(0),
                  a_mn ? 1 : 0, b_mn ? 1 : 0, out_mode, (int)ctas, (int)bn, A.device().index(), (int)max_ctas, gp, gcfg, dp,
-                 gate_err.has_value() ? gate_err->data_ptr<int>() : nullptr, stream_handle ? (cudaStream_t)stream_handle : stream()), "gemm2");
+                 gate_err.has_value() ? gate_err->data_ptr<int>() : nullptr, pdl ? 1 : 0,
+                 stream_handle ? (cudaStream_t)stream_handle : stream()), "gemm2");
   return C;
 }
 
@@ -352,7 +354,7 @@ std::vector<Tensor> lstm_seq_fwd(const Tensor& gx, const Tensor& w_h, const Tens
                         act.data_ptr(), c0.data_ptr<float>(), dbg.has_value() ? dbg->data_ptr() : nullptr, tiled.data_ptr(), T, B, H,
                         (unsigned int*)sync_ws.data_ptr<int>(), (int)variant, stream(), h0.data_ptr(),
                         in_gate.has_value() ? (const unsigned int*)in_gate->data_ptr<int>() : nullptr, (int)in_gate_tiles_n,
-                        extra_signal ? 1 : 0), "lstm_seq_fwd");
+                        extra_signal ? 1 : 0, 0), "lstm_seq_fwd");
   return {h_seq, c_seq, act};
 }
 
@@ -375,7 +377,7 @@ std::vector<Tensor> lstm_seq_bwd(const std::optional<Tensor>& dh_seq, const Tens
                         dh0.data_ptr<float>(), dc0.data_ptr<float>(), dbg.has_value() ? dbg->data_ptr() : nullptr, tiled.data_ptr(), T, B, H,
                         (unsigned int*)sync_ws.data_ptr<int>(), (int)variant, stream(),
                         in_gate.has_value() ? (const unsigned int*)in_gate->data_ptr<int>() : nullptr, (int)in_gate_tiles_n,
-                        extra_signal ? 1 : 0), "lstm_seq_bwd");
+                        extra_signal ? 1 : 0, 0), "lstm_seq_bwd");
   return {dpre, dh0, dc0};
 }
 
@@ -383,7 +385,7 @@ std::vector<Tensor> lstm_seq_bwd(const std::optional<Tensor>& dh_seq, const Tens
 // launch goes to an explicit stream - the caching allocator never sees a side stream.
 void lstm_seq_fwd_into(const Tensor& gx, const Tensor& w_h, const Tensor& bias, const Tensor& h0, const Tensor& c0, Tensor h_seq,
                        Tensor c_seq, Tensor act, Tensor tiled, Tensor sync_ws, int64_t variant, std::optional<Tensor> in_gate,
-                       int64_t in_gate_tiles_n, bool extra_signal, int64_t stream_handle) {
+                       int64_t in_gate_tiles_n, bool extra_signal, int64_t stream_handle, int64_t launch_flags) {
   chk_cuda(gx, "gx"); chk_cuda(w_h, "w_h"); chk_cuda(bias, "bias"); chk_cuda(h0, "h0"); chk_cuda(c0, "c0");
   chk_cuda(h_seq, "h_seq"); chk_cuda(c_seq, "c_seq"); chk_cuda(act, "act"); chk_cuda(tiled, "tiled");
   c10::cuda::CUDAGuard gd(gx.device());
@@ -395,12 +397,21 @@ void lstm_seq_fwd_into(const Tensor& gx, const Tensor& w_h, const Tensor& bias, 
                         act.data_ptr(), c0.data_ptr<float>(), nullptr, tiled.data_ptr(), T, B, H, (unsigned int*)sync_ws.data_ptr<int>(),
                         (int)variant, stream_handle ? (cudaStream_t)stream_handle : stream(), h0.data_ptr(),
                         in_gate.has_value() ? (const unsigned int*)in_gate->data_ptr<int>() : nullptr, (int)in_gate_tiles_n,
-                        extra_signal ? 1 : 0), "lstm_seq_fwd_into");
+                        extra_signal ? 1 : 0, (int)launch_flags), "lstm_seq_fwd_into");
+}
+
+// h_seq[0] <- h0, c_seq[0] <- c0, tile image of h0, step counters <- 0 (what lstm_seq_fwd does first unless launch_flags bit 0)
+void lstm_seq_prologue(const Tensor& h0, const Tensor& c0, Tensor h_seq, Tensor c_seq, Tensor tiled, Tensor sync_ws) {
+  chk_cuda(h0, "h0"); chk_cuda(c0, "c0"); chk_cuda(h_seq, "h_seq"); chk_cuda(c_seq, "c_seq"); chk_cuda(tiled, "tiled");
+  c10::cuda::CUDAGuard gd(h0.device());
+  TORCH_CHECK(h0.scalar_type() == torch::kBFloat16 && c0.scalar_type() == torch::kFloat32 && h0.dim() == 2, "h0 bf16 [B,H] / c0 fp32");
+  check(ts_lstm_seq_prologue(h0.data_ptr(), c0.data_ptr<float>(), h_seq.data_ptr(), c_seq.data_ptr<float>(), tiled.data_ptr(),
+                             (unsigned int*)sync_ws.data_ptr<int>(), (int)h0.size(0), (int)h0.size(1), stream()), "lstm_seq_prologue");
 }
 
 void lstm_seq_bwd_into(const std::optional<Tensor>& dh_seq, const Tensor& w_hT, const Tensor& act, const Tensor& c_seq, Tensor dpre,
                        Tensor dh0, Tensor dc0, Tensor tiled, Tensor sync_ws, int64_t variant, std::optional<Tensor> in_gate,
-                       int64_t in_gate_tiles_n, bool extra_signal, int64_t stream_handle) {
+                       int64_t in_gate_tiles_n, bool extra_signal, int64_t stream_handle, int64_t launch_flags) {
   chk_cuda(w_hT, "w_hT"); chk_cuda(act, "act"); chk_cuda(c_seq, "c_seq"); chk_cuda(dpre, "dpre"); chk_cuda(dh0, "dh0"); chk_cuda(dc0, "dc0");
   c10::cuda::CUDAGuard gd(act.device());
   int T = act.size(0), B = act.size(1), H = act.size(2) / 4;
@@ -410,7 +421,7 @@ void lstm_seq_bwd_into(const std::optional<Tensor>& dh_seq, const Tensor& w_hT, 
                         dh0.data_ptr<float>(), dc0.data_ptr<float>(), nullptr, tiled.data_ptr(), T, B, H, (unsigned int*)sync_ws.data_ptr<int>(),
                         (int)variant, stream_handle ? (cudaStream_t)stream_handle : stream(),
                         in_gate.has_value() ? (const unsigned int*)in_gate->data_ptr<int>() : nullptr, (int)in_gate_tiles_n,
-                        extra_signal ? 1 : 0), "lstm_seq_bwd_into");
+                        extra_signal ? 1 : 0, (int)launch_flags), "lstm_seq_bwd_into");
 }
 
 }  // namespace
@@ -447,16 +458,18 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm2", &gemm2, py::arg("A"), py::arg("B"), py::arg("bias") = py::none(), py::arg("out") = py::none(), py::arg("a_mn") = false,
         py::arg("b_mn") = false, py::arg("out_fp32") = false, py::arg("accumulate") = false, py::arg("ctas") = 2, py::arg("bn") = 256,
         py::arg("max_ctas") = 0, py::arg("gate") = py::none(), py::arg("gate_cfg") = std::vector<int64_t>{}, py::arg("done") = py::none(),
-        py::arg("gate_err") = py::none(), py::arg("stream") = 0);
+        py::arg("gate_err") = py::none(), py::arg("stream") = 0, py::arg("pdl") = false);
   m.def("lstm_seq_fwd", &lstm_seq_fwd, py::arg("gx"), py::arg("w_h"), py::arg("bias"), py::arg("h0"), py::arg("c0"),
         py::arg("sync_ws"), py::arg("variant") = 0, py::arg("dbg") = py::none(), py::arg("in_gate") = py::none(),
         py::arg("in_gate_tiles_n") = 0, py::arg("extra_signal") = false);
   m.def("lstm_seq_fwd_into", &lstm_seq_fwd_into, py::arg("gx"), py::arg("w_h"), py::arg("bias"), py::arg("h0"), py::arg("c0"),
         py::arg("h_seq"), py::arg("c_seq"), py::arg("act"), py::arg("tiled"), py::arg("sync_ws"), py::arg("variant"),
-        py::arg("in_gate") = py::none(), py::arg("in_gate_tiles_n") = 0, py::arg("extra_signal") = false, py::arg("stream") = 0);
+        py::arg("in_gate") = py::none(), py::arg("in_gate_tiles_n") = 0, py::arg("extra_signal") = false, py::arg("stream") = 0,
+        py::arg("launch_flags") = 0);
+  m.def("lstm_seq_prologue", &lstm_seq_prologue);
   m.def("lstm_seq_bwd_into", &lstm_seq_bwd_into, py::arg("dh_seq"), py::arg("w_hT"), py::arg("act"), py::arg("c_seq"), py::arg("dpre"),
         py::arg("dh0"), py::arg("dc0"), py::arg("tiled"), py::arg("sync_ws"), py::arg("variant"), py::arg("in_gate") = py::none(),
-        py::arg("in_gate_tiles_n") = 0, py::arg("extra_signal") = false, py::arg("stream") = 0);
+        py::arg("in_gate_tiles_n") = 0, py::arg("extra_signal") = false, py::arg("stream") = 0, py::arg("launch_flags") = 0);
   m.def("lstm_seq_bwd", &lstm_seq_bwd, py::arg("dh_seq"), py::arg("w_hT"), py::arg("act"), py::arg("c_seq"), py::arg("dhT"),
         py::arg("dcT"), py::arg("sync_ws"), py::arg("variant") = 0, py::arg("dbg") = py::none(), py::arg("in_gate") = py::none(),
         py::arg("in_gate_tiles_n") = 0, py::arg("extra_signal") = false);

@@ -48,6 +48,7 @@ struct ARArgs {
   int rank, world;
   float inv_world, lr, b1, b2, eps, wd;
   unsigned long long timeout_ns;
+  int pdl;                     // launched as a programmatic dependent: wait for the previous kernel of the stream before exiting
 };
 
 TS_DEVICE float4 ld_f4(const float* p) {
@@ -189,6 +190,7 @@ __global__ void __launch_bounds__(kThreads) ar_two_shot_kernel(const __grid_cons
   }
   cross_rank_barrier(a, ++epoch);              // every replica holds every slice
   if (threadIdx.x == 0) a.epochs[blockIdx.x] = epoch;
+  if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -223,6 +225,7 @@ __global__ void __launch_bounds__(kThreads) ar_one_shot_kernel(const __grid_cons
   }
   cross_rank_barrier(a, ++epoch);              // peers are done reading my input: it may be overwritten
   if (threadIdx.x == 0) a.epochs[blockIdx.x] = epoch;
+  if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // pdl: programmatic dependent launch - the kernel may start while the PREVIOUS kernel of the stream is still running (as soon
@@ -274,6 +277,7 @@ extern "C" int ts_fused_allreduce(const unsigned long long* ptrs, unsigned long 
   a.n4 = n / 4; a.rank = rank; a.world = world; a.inv_world = 1.0f / (float)world;
   a.lr = lr; a.b1 = b1; a.b2 = b2; a.eps = eps; a.wd = wd;
   a.timeout_ns = (unsigned long long)(timeout_s * 1e9);
+  a.pdl = pdl;
   if (multicast && (!mc_in || !mc_param)) multicast = 0;
   switch (mode) {
     case MODE_AVG: return launch_mode<MODE_AVG>(a, two_shot, multicast, blocks, pdl, st);

@@ -101,12 +101,13 @@ struct Gemm2Params {
   // Dataflow gate (layer wavefront): the rows of A are written by a persistent LSTM kernel that is still running.  Rows
   // [t * gate_rows_per_step, +gate_rows_per_step) belong to time step t; a tile may be loaded once ALL gate_count arrival
   // counters gate[i * gate_stride] have reached gate_base + gate_per_step * t, with t the last (gate_use_last) or first time
-  // step the tile touches.  done[(tile_m * tiles_n + tile_n) * kCtas + cta]++ publishes a finished 128-row output block.
+  // step the tile touches.  done[(row / 128) * tiles_n + tile_n]++ publishes a finished 128-row x BN output block.
   const unsigned int* gate;
   int gate_count, gate_stride, gate_base, gate_per_step, gate_rows_per_step, gate_use_last;
   long long gate_spin_limit;     // clock64 ticks before giving up (sets *gate_err)
   int* gate_err;
   unsigned int* done;
+  int pdl;                       // launched as a programmatic dependent of the previous kernel (see launch2); waits for it before exiting
   int reverse_m;                 // walk the M tiles from the last to the first (the backward recurrence runs backwards in time)
 };
 
@@ -342,7 +343,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         asm volatile("bar.sync 1, 128;" ::: "memory");           // all four epilogue warps have issued their stores
         if (ew == 0 && lane == 0)
           asm volatile("red.release.gpu.global.add.u32 [%0], 1;"
-                       ::"l"(p.done + ((size_t)tile_m_of(tile) * tiles_n + (tile % tiles_n)) * kCtas + crank) : "memory");
+                       ::"l"(p.done + ((size_t)tile_m_of(tile) * kCtas + crank) * tiles_n + (tile % tiles_n)) : "memory");
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -351,6 +352,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   tc::fence_before_sync();
   __syncthreads();
   if (kCtas == 2) cluster_sync2();               // nobody leaves while the pair's MMAs may still read its shared memory
+  if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (warp == 2) {
     if (kCtas == 2) tmem_dealloc2(tmem_base, C::kTmemCols); else tc::tmem_dealloc(tmem_base, C::kTmemCols);
   }
@@ -381,10 +383,15 @@ int launch2(const void* A, const void* B, const Gemm2Params& p, int lda, int ldb
   if (tiles < clusters) clusters = tiles;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * kCtas); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = C::kSmemBytes; cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = kCtas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
+  if (p.pdl) {
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   return (int)cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
 }
 
@@ -414,12 +421,12 @@ int launch_major(const void* A, const void* B, const Gemm2Params& p, int lda, in
 // gate_cfg[7] = {count, stride (u32 words), base, per_step, rows_per_step, use_last, reverse_m} (see Gemm2Params); max_ctas > 0 caps the grid.
 extern "C" int ts_gemm2(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, int lda, int ldb, int ldc,
                         int a_mn, int b_mn, int out_mode, int ctas, int bn, int dev, int max_ctas, const unsigned int* gate,
-                        const int* gate_cfg, unsigned int* done, int* gate_err, cudaStream_t st) {
+                        const int* gate_cfg, unsigned int* done, int* gate_err, int pdl, cudaStream_t st) {
   if (K % 8 != 0 || lda % 8 != 0 || ldb % 8 != 0) { ts::set_last_error("gemm2: K and the operand pitches must be multiples of 8"); return -2; }
   if ((a_mn && M % 8 != 0) || (b_mn && N % 8 != 0) || N % 8 != 0) { ts::set_last_error("gemm2: M (MN-major A) / N must be multiples of 8"); return -2; }
   Gemm2Params p{};
   p.C = C; p.bias = bias; p.M = M; p.N = N; p.K = K; p.ldc = ldc;
-  p.gate = gate; p.gate_err = gate_err; p.done = done;
+  p.gate = gate; p.gate_err = gate_err; p.done = done; p.pdl = pdl;
   if (gate != nullptr) {
     p.gate_count = gate_cfg[0]; p.gate_stride = gate_cfg[1]; p.gate_base = gate_cfg[2]; p.gate_per_step = gate_cfg[3];
     p.gate_rows_per_step = gate_cfg[4] > 0 ? gate_cfg[4] : 1; p.gate_use_last = gate_cfg[5]; p.reverse_m = gate_cfg[6];

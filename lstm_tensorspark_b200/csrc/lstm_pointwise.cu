@@ -200,19 +200,21 @@ __global__ void colsum_bf16_kernel(const uint4* __restrict__ src, float* __restr
 }
 }  // namespace
 
-// scratch: fp32 [slabs * cols] + u32 [cols / 256] tickets (zero before first use; the kernel leaves them zero)
+// scratch: u32 [kColsumTickets] tickets at a FIXED place (zero before first use; the kernel leaves them zero - partial sums of
+// another shape must never alias them) followed by fp32 [slabs * cols] partials
+constexpr int kColsumTickets = 4096;
 extern "C" long long ts_colsum_scratch_bytes(int rows, int cols) {
   const int rows_per_block = 512;
   const long long slabs = (rows + rows_per_block - 1) / rows_per_block;
-  return slabs * cols * 4 + (cols / 256) * 4;
+  return (long long)kColsumTickets * 4 + slabs * cols * 4;
 }
 
 extern "C" int ts_colsum_bf16(const void* src, float* out, void* scratch, int rows, int cols, cudaStream_t st) {
-  if (cols % 256 != 0) return -2;
+  if (cols % 256 != 0 || cols / 256 > kColsumTickets) return -2;
   const int rows_per_block = 512;
   dim3 grid(cols / 256, (rows + rows_per_block - 1) / rows_per_block);
-  float* partial = (float*)scratch;
-  unsigned int* tickets = (unsigned int*)((char*)scratch + (size_t)grid.y * cols * 4);
+  unsigned int* tickets = (unsigned int*)scratch;
+  float* partial = (float*)((char*)scratch + (size_t)kColsumTickets * 4);
   colsum_bf16_kernel<<<grid, 256, 0, st>>>((const uint4*)src, out, partial, tickets, rows, cols, rows_per_block);
   return (int)cudaGetLastError();
 }

@@ -222,8 +222,11 @@ struct SeqParams {
   int poll_acquire;            // experiment: ld.acquire polls instead of relaxed
   // Layer wavefront (two layers' recurrences co-resident, chained through a dataflow-gated GEMM on the idle SMs):
   const unsigned int* in_gate; // completion counters of the GEMM that produces gx (fwd) / dh_seq (bwd) tile by tile while this kernel
-                               // runs: [(row / 256) * in_gate_tiles_n + col / 256][(row % 256) / 128]; null = the operand is complete
+                               // runs: [(row / 128) * in_gate_tiles_n + col / 256]; null = the operand is complete
   int in_gate_tiles_n;
+  int pdl_wait;                // launched as a programmatic dependent: before exiting, wait for the grids launched before this one
+                               // (completion of the chain's LAST kernel then implies completion of all of them)
+  int no_trap;                 // debugging: the watchdog only records the abort (variant bit 20) instead of killing the kernel
   int extra_signal;            // one more arrival on this CTA's k-block counter after the LAST step's bookkeeping stores (a gated
                                // GEMM consumes h_seq / dpre in the natural layout, which is written after the per-step signal)
 };
@@ -536,7 +539,8 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
         else if (clock64() - t_abort > kAbortGrace) {
           if (lane == 0) atomicExch(reinterpret_cast<int*>(p.sync + kSyncErr), 2);
           __threadfence_system();
-          __trap();
+          if (!p.no_trap) __trap();
+          break;
         }
       }
     }
@@ -591,7 +595,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
           U8 gxw[2];
           if (p.in_gate != nullptr) {                 // wavefront: gx[t] is produced while we run (this warp's rows: one 128-row block)
             const size_t gr = (size_t)t * B + (size_t)mb * BM;
-            ok = wait_in_gate(p.in_gate + ((gr >> 8) * p.in_gate_tiles_n + (n0 >> 8)) * 2 + ((gr >> 7) & 1), lane, abort_flag);
+            ok = wait_in_gate(p.in_gate + (gr >> 7) * p.in_gate_tiles_n + (n0 >> 8), lane, abort_flag);
             if (!ok) break;
             if (valid) {
               const __nv_bfloat16* gp = p.gx + ((size_t)t * B + row) * (4 * H) + n0;
@@ -753,7 +757,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
           uint4 dhv;
           if (p.in_gate != nullptr && s < p.T) {      // wavefront: dh_seq[t] (= dX of the layer above) is produced while we run
             const size_t gr = (size_t)t * B + (size_t)mb * BM;
-            ok = wait_in_gate(p.in_gate + ((gr >> 8) * p.in_gate_tiles_n + (j0 >> 8)) * 2 + ((gr >> 7) & 1), lane, abort_flag);
+            ok = wait_in_gate(p.in_gate + (gr >> 7) * p.in_gate_tiles_n + (j0 >> 8), lane, abort_flag);
             if (!ok) break;
           }
           if (valid && s < p.T) {
@@ -890,6 +894,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
   tc::fence_before_sync();
   __syncthreads();
   if (kCluster) cluster_sync_all();              // nobody exits while a peer may still write into / arrive on its smem
+  if (p.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (threadIdx.x == 0 && ss->abort_flag) atomicExch(reinterpret_cast<int*>(p.sync + kSyncErr), 1);
   if (warp == 2) tc::tmem_dealloc(tmem_d, kTmemCols);
 }
@@ -934,7 +939,7 @@ int launch_cfg(const CUtensorMap& tw, const SeqParams& p, int grid, cudaStream_t
   if (e != cudaSuccess) return (int)e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = kClusterDim; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
@@ -943,6 +948,11 @@ int launch_cfg(const CUtensorMap& tw, const SeqParams& p, int grid, cudaStream_t
     e = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
     if (e != cudaSuccess) { cudaGetLastError(); return -20; }
     if (nclusters * kClusterDim < grid) return -21;    // not co-resident
+  }
+  if (p.pdl_wait) {                                    // start as soon as the previous kernel of the stream is fully resident
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
   }
   e = cudaLaunchKernelEx(&cfg, kern, tw, p);
   return (int)e;
@@ -1009,6 +1019,7 @@ static int seq_common(SeqParams& p, const void* w_base, int variant, cudaStream_
   p.debug_mode = (variant >> 12) & 7;
   p.sync_mode = (variant >> 16) & 3;
   p.poll_acquire = (variant >> 18) & 1;
+  p.no_trap = (variant >> 20) & 1;
   if (tiles != 2 || tiles_m % 2 != 0) tiles = 1;
   // resident weight slice if it fits next to >= 4 ring stages, else stream the weights through the ring
   const bool stream = smem_bytes(H, kBwd, 4, 1) > 227 * 1024 || ((variant >> 8) & 1);
@@ -1043,8 +1054,8 @@ static int seq_common(SeqParams& p, const void* w_base, int variant, cudaStream_
 
 extern "C" int ts_lstm_seq_fwd(const void* gx, const void* w_h, const float* bias, const void* h_seq, const float* c_seq,
                                void* act, const float* c0, void* dbg, void* a_tiled, int T, int B, int H, unsigned int* sync_ws, int variant,
-                               cudaStream_t st, const void* h0, const unsigned int* in_gate, int in_gate_tiles_n, int extra_signal) {
-  {
+                               cudaStream_t st, const void* h0, const unsigned int* in_gate, int in_gate_tiles_n, int extra_signal, int launch_flags) {
+  if (!(launch_flags & 1)) {           // bit 0: the caller has run ts_lstm_seq_prologue itself (wavefront: all prologues precede the chain)
     const int tiles_m = (B + BM - 1) / BM;
     const int total = tiles_m * BM * (H / 8);
     int blocks = (total + 255) / 256;
@@ -1057,18 +1068,30 @@ extern "C" int ts_lstm_seq_fwd(const void* gx, const void* w_h, const float* bia
   p.gx = (const __nv_bfloat16*)gx; p.bias = bias; p.h_seq = (__nv_bfloat16*)h_seq; p.c_seq = (float*)c_seq;
   p.act = (__nv_bfloat16*)act; p.sync = sync_ws; p.T = T; p.B = B; p.H = H; p.dbg = (unsigned long long*)dbg;
   p.in_gate = in_gate; p.in_gate_tiles_n = in_gate_tiles_n; p.extra_signal = extra_signal;
+  p.pdl_wait = (launch_flags >> 1) & 1;
   return seq_common<false>(p, w_h, variant, st);
+}
+
+extern "C" int ts_lstm_seq_prologue(const void* h0, const float* c0, void* h_seq, float* c_seq, void* a_tiled, unsigned int* sync_ws,
+                                    int B, int H, cudaStream_t st) {
+  const int tiles_m = (B + BM - 1) / BM;
+  const int total = tiles_m * BM * (H / 8);
+  int blocks = (total + 255) / 256;
+  if (blocks > 592) blocks = 592;
+  seq_prologue_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)h0, c0, (__nv_bfloat16*)h_seq, c_seq, (__nv_bfloat16*)a_tiled, sync_ws, B, H, tiles_m);
+  return (int)cudaGetLastError();
 }
 
 extern "C" int ts_lstm_seq_bwd(const void* dh_seq, const void* w_hT, const void* act, const float* c_seq, const void* dpre,
                                float* dh0, float* dc0, void* dbg, void* a_tiled, int T, int B, int H, unsigned int* sync_ws, int variant,
-                               cudaStream_t st, const unsigned int* in_gate, int in_gate_tiles_n, int extra_signal) {
-  cudaMemsetAsync(sync_ws, 0, kSyncErr * sizeof(unsigned int), st);      // arrival counters restart at 0 every launch
+                               cudaStream_t st, const unsigned int* in_gate, int in_gate_tiles_n, int extra_signal, int launch_flags) {
+  if (!(launch_flags & 1)) cudaMemsetAsync(sync_ws, 0, kSyncErr * sizeof(unsigned int), st);      // arrival counters restart at 0 every launch
   SeqParams p{};
   p.a_tiled = (__nv_bfloat16*)a_tiled;
   p.dh_seq = (const __nv_bfloat16*)dh_seq; p.act = (__nv_bfloat16*)act; p.c_seq = (float*)c_seq; p.dpre = (__nv_bfloat16*)dpre;
   p.dh0 = dh0; p.dc0 = dc0; p.sync = sync_ws; p.T = T; p.B = B; p.H = H; p.dbg = (unsigned long long*)dbg;
   p.in_gate = in_gate; p.in_gate_tiles_n = in_gate_tiles_n; p.extra_signal = extra_signal;
+  p.pdl_wait = (launch_flags >> 1) & 1;
   return seq_common<true>(p, w_hT, variant, st);
 }
 

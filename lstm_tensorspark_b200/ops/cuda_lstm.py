@@ -334,6 +334,24 @@ def _side_streams(device):
     return _SIDE_STREAMS[key]
 
 
+_WARM = set()
+
+
+def _warm_wavefront_kernels(device):
+    """CUDA loads kernels lazily, and loading one may wait for every running kernel to finish.  The wavefront's kernels WAIT
+    FOR EACH OTHER on the device, so a kernel that is loaded for the first time while its producers are already spinning would
+    deadlock (until the bounded spins time out).  Load the gated GEMM instantiations once, before the first concurrent use."""
+    if device.index in _WARM:
+        return
+    a = torch.zeros(256, 64, dtype=torch.bfloat16, device=device)
+    w = torch.zeros(256, 64, dtype=torch.bfloat16, device=device)
+    wt = torch.zeros(64, 256, dtype=torch.bfloat16, device=device)
+    ext().gemm2(a, w, ctas=1, bn=256)
+    ext().gemm2(a, wt, b_mn=True, ctas=1, bn=256)
+    torch.cuda.synchronize(device)
+    _WARM.add(device.index)
+
+
 def _pair_ws(device, tag: str, n_done: int):
     """[sync ws of the head kernel | sync ws of the tail kernel | completion counters of the gated GEMM] in one allocation."""
     key = (device.index, tag)
@@ -371,8 +389,8 @@ class _LSTMPairFn(torch.autograd.Function):
         ba_f, bb_f = b_a.detach().float().contiguous(), b_b.detach().float().contiguous()
         h0a_c, h0b_c = h0a.detach().to(cd).contiguous(), h0b.detach().to(cd).contiguous()
         c0a_f, c0b_f = c0a.detach().float().contiguous(), c0b.detach().float().contiguous()
+        _warm_wavefront_kernels(dev)
         gx_a = _gemm_tn(x2d, wxa).view(T, B, 4 * Ha)
-        # every buffer is allocated here, on the main stream, before the fork
         opt = dict(dtype=cd, device=dev)
         h_seq_a = torch.empty(T + 1, B, Ha, **opt); c_seq_a = torch.empty(T + 1, B, Ha, dtype=torch.float32, device=dev)
         act_a = torch.empty(T, B, 4 * Ha, **opt); til_a = torch.empty((T + 1) * 2 * 128 * Ha, **opt)
@@ -381,23 +399,20 @@ class _LSTMPairFn(torch.autograd.Function):
         gx_b = torch.empty(T, B, 4 * Hb, **opt)
         tn = 4 * Hb // 256
         ws_a, ws_b, done = _pair_ws(dev, "fwd", T * tn * 2)
-        ws_a[:SYNC_WORDS - 1].zero_(); ws_b[:SYNC_WORDS - 1].zero_(); done.zero_()
+        done.zero_()                                                     # (the prologue kernels zero ws_a / ws_b)
         var = (SEQ_VARIANT & ~15) | 2                                    # two batch tiles per CTA: 64 CTAs per layer at H = 1024
-        main = torch.cuda.current_stream(dev)
-        s_gemm, s_tail = _side_streams(dev)
-        ev = torch.cuda.Event()
-        ev.record(main)
-        s_gemm.wait_event(ev)
-        s_tail.wait_event(ev)
-        # launch order = dependency order of the chain heads: L_a (nothing to wait for), L_b, then the GEMM on what is left
-        E.lstm_seq_fwd_into(gx_a, wha, ba_f, h0a_c, c0a_f, h_seq_a, c_seq_a, act_a, til_a, ws_a, var, None, 0, True, main.cuda_stream)
-        E.lstm_seq_fwd_into(gx_b, whb, bb_f, h0b_c, c0b_f, h_seq_b, c_seq_b, act_b, til_b, ws_b, var, done, tn, False, s_tail.cuda_stream)
-        free_ctas = max(2, (_sms(dev) - Ha // 16 - Hb // 16) // 2 * 2)
-        E.gemm2(h_seq_a[1:].view(T * B, Ha), wxb, out=gx_b.view(T * B, 4 * Hb), ctas=2, bn=256, max_ctas=free_ctas,
-                gate=ws_a[512:], gate_cfg=[2 * (Ha // 64), 32, 8, 4, B, 1, 0], done=done, gate_err=ws_a[SYNC_WORDS - 1:], stream=s_gemm.cuda_stream)
-        e1, e2 = torch.cuda.Event(), torch.cuda.Event()
-        e1.record(s_gemm); e2.record(s_tail)
-        main.wait_event(e1); main.wait_event(e2)
+        # ONE stream, a programmatic-dependent-launch chain: L_a -> L_b (starts once every CTA of L_a is resident) -> gated GEMM
+        # (starts once every CTA of L_b is resident, on the SMs that are left).  The order in which the three grids take their
+        # SMs is thereby fixed (a kernel that is still queueing could otherwise starve the chain head of co-resident SMs).
+        # Everything the later kernels need up front (prologues, zeroed counters) is enqueued before the chain head.
+        E.lstm_seq_prologue(h0a_c, c0a_f, h_seq_a, c_seq_a, til_a, ws_a)
+        E.lstm_seq_prologue(h0b_c, c0b_f, h_seq_b, c_seq_b, til_b, ws_b)
+        E.lstm_seq_fwd_into(gx_a, wha, ba_f, h0a_c, c0a_f, h_seq_a, c_seq_a, act_a, til_a, ws_a, var, None, 0, True, 0, 1)
+        E.lstm_seq_fwd_into(gx_b, whb, bb_f, h0b_c, c0b_f, h_seq_b, c_seq_b, act_b, til_b, ws_b, var, done, tn, False, 0, 3)
+        # single-CTA tiles: the recurrences' CTAs are spread one per TPC, the SMs they leave free rarely form CTA pairs
+        free_ctas = max(1, _sms(dev) - Ha // 16 - Hb // 16)
+        E.gemm2(h_seq_a[1:].view(T * B, Ha), wxb, out=gx_b.view(T * B, 4 * Hb), ctas=1, bn=256, max_ctas=free_ctas,
+                gate=ws_a[512:], gate_cfg=[2 * (Ha // 64), 32, 8, 4, B, 1, 0], done=done, gate_err=ws_a[SYNC_WORDS - 1:], pdl=True)
         STATS["fast_fwd"] += 2
         STATS["kernels"] += 3
         STATS["wavefront_fwd"] = STATS.get("wavefront_fwd", 0) + 1
@@ -427,21 +442,12 @@ class _LSTMPairFn(torch.autograd.Function):
         ws_b, ws_a, done = _pair_ws(dev, "bwd", T * tn * 2)               # head of the backward chain is layer b
         ws_a[:SYNC_WORDS - 1].zero_(); ws_b[:SYNC_WORDS - 1].zero_(); done.zero_()
         var = (SEQ_VARIANT & ~15) | 2
-        main = torch.cuda.current_stream(dev)
-        s_gemm, s_tail = _side_streams(dev)
-        ev = torch.cuda.Event()
-        ev.record(main)
-        s_gemm.wait_event(ev)
-        s_tail.wait_event(ev)
-        E.lstm_seq_bwd_into(dh_seq_b, whT_b, act_b, c_seq_b, dpre_b, dh0b, dc0b, til_b, ws_b, var, None, 0, True, main.cuda_stream)
-        E.lstm_seq_bwd_into(dx_b, whT_a, act_a, c_seq_a, dpre_a, dh0a, dc0a, til_a, ws_a, var, done, tn, False, s_tail.cuda_stream)
-        free_ctas = max(2, (_sms(dev) - Ha // 16 - Hb // 16) // 2 * 2)
-        E.gemm2(dpre_b.view(T * B, 4 * Hb), wxb, out=dx_b.view(T * B, Ha), b_mn=True, ctas=2, bn=256, max_ctas=free_ctas,
-                gate=ws_b[512:], gate_cfg=[2 * (4 * Hb // 64), 32, T + 1, -1, B, 0, 1], done=done, gate_err=ws_b[SYNC_WORDS - 1:],
-                stream=s_gemm.cuda_stream)
-        e1, e2 = torch.cuda.Event(), torch.cuda.Event()
-        e1.record(s_gemm); e2.record(s_tail)
-        main.wait_event(e1); main.wait_event(e2)
+        # programmatic-dependent-launch chain on one stream (see forward): L_b -> L_a -> gated dX GEMM
+        E.lstm_seq_bwd_into(dh_seq_b, whT_b, act_b, c_seq_b, dpre_b, dh0b, dc0b, til_b, ws_b, var, None, 0, True, 0, 1)
+        E.lstm_seq_bwd_into(dx_b, whT_a, act_a, c_seq_a, dpre_a, dh0a, dc0a, til_a, ws_a, var, done, tn, False, 0, 3)
+        free_ctas = max(1, _sms(dev) - Ha // 16 - Hb // 16)
+        E.gemm2(dpre_b.view(T * B, 4 * Hb), wxb, out=dx_b.view(T * B, Ha), b_mn=True, ctas=1, bn=256, max_ctas=free_ctas,
+                gate=ws_b[512:], gate_cfg=[2 * (4 * Hb // 64), 32, T + 1, -1, B, 0, 1], done=done, gate_err=ws_b[SYNC_WORDS - 1:], pdl=True)
         STATS["fast_bwd"] += 2
         STATS["kernels"] += 5
         a = ctx.addrs
