@@ -353,7 +353,7 @@ def main():
         torch.cuda.synchronize(device)
         launches = cuda_ext.LAUNCHES["n"] - k0          # our kernels per step (counted at the binding layer, eager step)
         graphed, graph_err = False, None
-        want_graph = args.cuda_graph == 1 or (args.cuda_graph < 0 and world == 1)
+        want_graph = args.cuda_graph != 0           # default: capture the whole step (fwd + bwd + fused allreduce/update) once, replay it
         if want_graph:
             try:
                 eng.capture(dev_x[:B], dev_y[:B])

@@ -14,7 +14,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _run(args, timeout=600):
     env = dict(os.environ, PYTHONPATH=ROOT)
     r = subprocess.run([sys.executable] + args, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
-    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
+    if r.returncode != 0:
+        print("STDOUT", r.stdout[-3000:])
+        print("STDERR", r.stderr[-6000:])
+    assert r.returncode == 0, r.returncode
     return r
 
 
