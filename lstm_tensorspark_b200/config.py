@@ -66,7 +66,7 @@ class Config:
     deterministic: bool = False         # bit-reproducible runs: the recurrence kernels consume operand blocks in index order (not
                                         # arrival order), so fp32 accumulation order is fixed (a few % slower)
     grad_buckets: bool = True           # fused comm, grad_allreduce: per-layer buckets synced under the lower layers' backward
-    grad_bucket_blocks: int = 32        # CTAs of an overlapped bucket launch (it runs on the SMs the recurrence leaves idle)
+    grad_bucket_blocks: int = 64        # CTAs of an overlapped bucket launch (it runs on the SMs the recurrence leaves idle)
     fault_inject: str = ""              # "rank:step" => that rank exits abnormally at that step (test hook)
     timeout_s: float = 600.0
     quiet: bool = False

@@ -33,6 +33,7 @@ int ts_cast_bf16(const float*, void*, long long, cudaStream_t);
 int ts_fused_allreduce(const unsigned long long*, unsigned long long, unsigned long long, unsigned long long, float*,
                        float*, unsigned int*, int*, long long, int, int, int, int, int, int, float, float, float, float,
                        float, double, cudaStream_t, int*, long long, int, int);
+int ts_ar_bump_step(int*, cudaStream_t);
 int ts_ar_max_blocks();
 int ts_ar_flag_words();
 int ts_head_fwd_tc(const void*, int, const float*, const float*, const long long*, float*, float*, float*, int*, int, int, int, cudaStream_t);
@@ -451,6 +452,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("two_shot"), py::arg("multicast"), py::arg("blocks"), py::arg("lr"), py::arg("b1"), py::arg("b2"), py::arg("eps"),
         py::arg("wd"), py::arg("timeout_s"), py::arg("step_dev") = py::none(), py::arg("wd_numel") = -1, py::arg("bump_step") = true,
         py::arg("pdl") = false);
+  m.def("ar_bump_step", [](Tensor step_dev) {
+    TORCH_CHECK(step_dev.is_cuda() && step_dev.scalar_type() == torch::kInt32, "ar_bump_step: int32 cuda tensor");
+    c10::cuda::CUDAGuard gd(step_dev.device());
+    check(ts_ar_bump_step(step_dev.data_ptr<int>(), stream()), "ar_bump_step");
+  });
   m.def("ar_max_blocks", []() { return ts_ar_max_blocks(); });
   m.def("ar_flag_words", []() { return ts_ar_flag_words(); });
   m.def("gemm_generic", &gemm_generic, py::arg("A"), py::arg("B"), py::arg("bias") = py::none(), py::arg("out") = py::none(),

@@ -234,6 +234,9 @@ __global__ void __launch_bounds__(kThreads) ar_one_shot_kernel(const __grid_cons
 // previous kernel writes, so it never executes griddepcontrol.wait.
 template <typename K>
 int launch_k(K kern, const ARArgs& a, int blocks, int pdl, cudaStream_t st) {
+  // no shared memory of our own, but ask for the max-shared L1 split: the split the tensor-core kernels run with, so that
+  // these CTAs can be co-resident with a weight-gradient GEMM on the same SMs (see gemm2_tcgen05.cu)
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
   cudaLaunchAttribute at[1];
@@ -285,6 +288,13 @@ extern "C" int ts_fused_allreduce(const unsigned long long* ptrs, unsigned long 
     case MODE_ADAM: return launch_mode<MODE_ADAM>(a, two_shot, multicast, blocks, pdl, st);
   }
   return -3;
+}
+
+// Adam's device-resident step counter += 1 (once per optimizer step, BEFORE backward: a launch of its own between a
+// weight-gradient GEMM and a bucket's allreduce would serialise the two)
+extern "C" int ts_ar_bump_step(int* step_dev, cudaStream_t st) {
+  ar_inc_step_kernel<<<1, 1, 0, st>>>(step_dev);
+  return (int)cudaGetLastError();
 }
 
 extern "C" int ts_ar_max_blocks() { return kMaxBlocks; }

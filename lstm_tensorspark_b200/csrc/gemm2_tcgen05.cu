@@ -128,6 +128,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // A kernel queued behind this one with the programmatic-dependent-launch attribute (a finished gradient bucket's fused
+  // allreduce + update) may start once this grid is resident: it shares the SMs instead of waiting for the GEMM to drain.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t crank = kCtas == 2 ? cluster_ctarank2() : 0u;
   const bool leader = crank == 0;
   constexpr int TM = BM * kCtas;                              // tile rows per cluster
@@ -372,6 +375,9 @@ int launch2(const void* A, const void* B, const Gemm2Params& p, int lda, int ldb
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) return (int)e;
+    // same L1 / shared-memory split as the fused allreduce kernels: an SM only runs CTAs of two kernels at once when they
+    // agree on it, and a gradient bucket's allreduce is launched (programmatic dependent) to run next to this GEMM
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr_set = true;
   }
   const int TM = BM * kCtas;

@@ -23,6 +23,11 @@ from .ops.optim import FlatOptimizer
 from .parallel.comm import Communicator
 
 
+import os as _os
+
+_BUCKET_PDL = _os.environ.get("LSTM_TS_BUCKET_PDL", "1") == "1"      # 0: buckets in plain stream order (no overlap) - for A/B timing
+
+
 class TrainEngine:
     def __init__(self, cfg: Config, rank: int = 0, world_size: int = 1, comm: Optional[Communicator] = None,
                  batch_size: Optional[int] = None, device: Optional[torch.device] = None,
@@ -80,17 +85,21 @@ class TrainEngine:
             return None
         off = {id(p): o for p, o in zip(flat.params, flat.offsets)}
         layers = list(self.model.rnn.layers)
-        starts = [off[id(l.w_x)] for l in layers] + [flat.lstm_numel]
         others = [p for p in flat.params[len(self.model.rnn.averaged_parameters()):]]
         others_direct = all(p.data_ptr() in flat._direct for p in others)
+        end = [off[id(l.w_x)] for l in layers[1:]] + [flat.lstm_numel]        # end of each layer's segment
         plan = []
         for li in reversed(range(len(layers))):
-            lo, hi = starts[li], starts[li + 1]
-            need = [layers[li].w_x, layers[li].w_h, layers[li].bias]
+            l = layers[li]
+            # [w_h, bias] finishes with the layer's bias gradient, [w_x] already with its weight-gradient GEMM: two buckets per
+            # layer, each launched under the GEMM / recurrence kernel that follows it in backward
+            lo_x, lo_h, hi = off[id(l.w_x)], off[id(l.w_h)], end[li]
+            need_h = [l.w_h, l.bias]
             if li == len(layers) - 1 and others_direct:
                 hi = flat.padded_numel                     # head weights / bias follow the last layer in the flat buffer
-                need = need + others
-            plan.append({"lo": lo, "hi": hi, "need": {p.data_ptr() for p in need}})
+                need_h = need_h + others
+            plan.append({"lo": lo_x, "hi": lo_h, "need": {l.w_x.data_ptr()}})
+            plan.append({"lo": lo_h, "hi": hi, "need": {p.data_ptr() for p in need_h}})
         if not others_direct:
             plan.append({"lo": flat.lstm_numel, "hi": flat.padded_numel, "need": None})    # autograd-accumulated: only final at the end
         return plan
@@ -102,20 +111,20 @@ class TrainEngine:
         state = {"next": 0}
 
         def ready():
-            # queue every leading bucket whose parameters have all been written; it is launched (PDL) right after the next
-            # persistent backward kernel of a lower layer, i.e. it overlaps that recurrence
+            # queue every leading bucket whose parameters have all been written; it is launched (PDL) right after the next big
+            # backward kernel (weight-gradient GEMM / lower layer's recurrence), i.e. it runs next to that kernel
             while state["next"] < len(plan) - 1:
                 b = plan[state["next"]]
                 if b["need"] is None or (b["need"] & flat._stale):
                     break
-                cuda_lstm.AFTER_SEQ_BWD.append(lambda b=b: comm.launch_bucket(b["lo"], b["hi"], pdl=True, blocks=self.cfg.grad_bucket_blocks))
+                cuda_lstm.AFTER_SEQ_BWD.append(lambda b=b: comm.launch_bucket(b["lo"], b["hi"], pdl=_BUCKET_PDL, blocks=self.cfg.grad_bucket_blocks))
                 state["next"] += 1
 
-        cuda_lstm.HOOKS["layer_grads_ready"] = ready
+        cuda_lstm.HOOKS["grads_written"] = ready
         try:
             loss.backward()
         finally:
-            cuda_lstm.HOOKS["layer_grads_ready"] = None
+            cuda_lstm.HOOKS["grads_written"] = None
         flat.finalize_grads()
         while cuda_lstm.AFTER_SEQ_BWD:                      # queued but no lower recurrence followed (generic path)
             cuda_lstm.AFTER_SEQ_BWD.pop(0)()
@@ -127,15 +136,18 @@ class TrainEngine:
         loss, _logits, _correct = self.model(x, y)
         if self._wd_autograd:
             loss = loss + torch.stack([fn(v) * wd for (v, fn, wd) in self._wd_autograd]).sum()
-        loss.backward()
+        if self._bucket_plan:
+            self._backward_with_buckets(loss)      # backward + per-bucket fused allreduce / update, overlapped with backward
+        else:
+            loss.backward()
+            self.flat.finalize_grads()
+            if self.sync_grads:
+                self.comm.grad_step_(self.flat, self.optimizer)
+            else:
+                self.optimizer.step()
         if self._wd_in_kernel:                 # reported total loss includes the L2 value; its gradient is applied by the update kernel
             with torch.no_grad():
                 loss = loss.detach() + torch.stack([fn(v) * wd for (v, fn, wd) in self._wd_in_kernel]).sum()
-        self.flat.finalize_grads()
-        if self.sync_grads:
-            self.comm.grad_step_(self.flat, self.optimizer)
-        else:
-            self.optimizer.step()
         return loss.detach()
 
     def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:

@@ -30,12 +30,24 @@ GEMM_VARIANT = int(os.environ.get("LSTM_TS_GEMM_VARIANT", "1"))   # 0: 128x128 t
 STATS = {"fast_fwd": 0, "fast_bwd": 0, "generic_fwd": 0, "generic_bwd": 0, "tc_gemm": 0, "kernels": 0}
 
 
-# Gradient-bucket overlap (engine.TrainEngine + parallel/fused_comm.py): LAYER_GRADS_READY is called after a layer's backward
-# has written its weight / bias gradients; callables queued in AFTER_SEQ_BWD are run right after the NEXT persistent backward
-# kernel has been launched (they launch a finished bucket's fused allreduce + update with programmatic dependent launch, so it
-# runs on the SMs that kernel leaves idle).
-HOOKS = {"layer_grads_ready": None}
+# Gradient-bucket overlap (engine.TrainEngine + parallel/fused_comm.py): HOOKS["grads_written"] is called after every weight /
+# bias gradient has been written; callables queued in AFTER_SEQ_BWD are run right after the NEXT big backward kernel has been
+# launched (a persistent recurrence kernel or a weight-gradient GEMM: both execute griddepcontrol.launch_dependents).  They
+# launch a finished bucket's fused allreduce + update as a programmatic dependent, so it runs NEXT TO that kernel (on the SMs
+# the recurrence leaves idle / co-resident with the GEMM's CTAs) instead of after it.
+HOOKS = {"grads_written": None}
 AFTER_SEQ_BWD = []
+
+
+def _after_big_launch():
+    while AFTER_SEQ_BWD:
+        AFTER_SEQ_BWD.pop(0)()
+
+
+def _grads_written():
+    h = HOOKS["grads_written"]
+    if h is not None and not _CHUNKING["on"]:
+        h()
 
 _PARAMS = {}          # fp32 param address -> (bf16 shadow view, fp32 grad view), maintained by models.flat.FlatParams
 DIRECT_GRADS = os.environ.get("LSTM_TS_DIRECT_GRADS", "1") == "1"
@@ -86,6 +98,8 @@ def _accumulate_grad(w_addr: int, a_t: torch.Tensor, b: torch.Tensor):
     sink = grad_sink(w_addr)
     if sink is not None:
         G.matmul(a_t, b.t(), out=sink[0], accumulate=sink[1])
+        _after_big_launch()                  # finished buckets of earlier gradients: allreduce them under this GEMM
+        _grads_written()
         return None
     return G.matmul(a_t, b.t(), out_dtype=torch.float32)
 
@@ -98,11 +112,13 @@ def _bias_grad(b_addr: int, dg2d: torch.Tensor):
         STATS["kernels"] += 1
         if sink is not None:
             ext().colsum_bf16_into(dg2d, sink[0], not sink[1])
+            _grads_written()
             return None
         return ext().colsum_bf16(dg2d)
     ones = torch.ones(1, dg2d.shape[0], dtype=dg2d.dtype, device=dg2d.device)
     if sink is not None:
         G.matmul(ones, dg2d.t(), out=sink[0].view(1, -1), accumulate=sink[1])
+        _grads_written()
         return None
     return G.matmul(ones, dg2d.t(), out_dtype=torch.float32).view(-1)
 
@@ -262,8 +278,7 @@ class _LSTMSeqFn(torch.autograd.Function):
             dpre, dh0, dc0 = E.lstm_seq_bwd(dh_seq, w_hT, act, c_seq, dhT, dcT, _sync_ws(dev), SEQ_VARIANT)
             STATS["fast_bwd"] += 1
             STATS["kernels"] += 1
-            while AFTER_SEQ_BWD:                 # finished gradient buckets of the layers above: sync them under this recurrence
-                AFTER_SEQ_BWD.pop(0)()
+            _after_big_launch()                  # finished gradient buckets of the layers above: sync them under this recurrence
         else:
             dpre = torch.empty_like(act)
             dh_rec: Optional[torch.Tensor] = dhT if dh_T is not None else None
@@ -284,8 +299,6 @@ class _LSTMSeqFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = G.matmul(dg2d, w_x_c.t(), out_dtype=cd).view(T, B, D)        # dG · W_x: W_x read in place as an MN-major operand
             STATS["kernels"] += 1
-        if HOOKS["layer_grads_ready"] is not None and ctx.whole_batch:
-            HOOKS["layer_grads_ready"]()
         h0_dt, c0_dt = ctx.in_dtypes
         return dx, dh0.to(h0_dt), dc0.to(c0_dt), dw_x, dw_h, db
 
@@ -451,13 +464,10 @@ class _LSTMPairFn(torch.autograd.Function):
         STATS["fast_bwd"] += 2
         STATS["kernels"] += 5
         a = ctx.addrs
-        hook = HOOKS["layer_grads_ready"]
         dg_b = dpre_b.view(T * B, 4 * Hb)
         dw_xb = _accumulate_grad(a[3], dg_b.t(), h_seq_a[1:].reshape(T * B, Ha))
         dw_hb = _accumulate_grad(a[4], dg_b.t(), h_seq_b[:T].reshape(T * B, Hb))
         db_b = _bias_grad(a[5], dg_b)
-        if hook is not None:
-            hook()
         dg_a = dpre_a.view(T * B, 4 * Ha)
         dw_xa = _accumulate_grad(a[0], dg_a.t(), x2d)
         dw_ha = _accumulate_grad(a[1], dg_a.t(), h_seq_a[:T].reshape(T * B, Ha))
@@ -466,8 +476,6 @@ class _LSTMPairFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = G.matmul(dg_a, wxa.t(), out_dtype=cd).view(T, B, D)
             STATS["kernels"] += 1
-        if hook is not None:
-            hook()
         t = ctx.in_dtypes
         return dx, dh0a.to(t[0]), dc0a.to(t[1]), dw_xa, dw_ha, db_a, dh0b.to(t[2]), dc0b.to(t[3]), dw_xb, dw_hb, db_b
 

@@ -163,7 +163,9 @@ class FusedComm(TorchDistComm):
     # -- bucketed gradient sync: a bucket's allreduce + update is launched as soon as its gradients are final ----------
     def begin_grad_step(self, flat: FlatParams, optimizer):
         optimizer.step_count += 1
-        self._gs = {"opt": optimizer, "bump": True, "buckets": []}
+        if optimizer.kind == "adam" and optimizer.step_dev is not None:
+            ext().ar_bump_step(optimizer.step_dev)          # here, not inside a bucket launch (see csrc/fused_allreduce.cu)
+        self._gs = {"opt": optimizer, "bump": False, "buckets": []}
         if optimizer.kind == "adam":
             self._state_buckets = self._gs["buckets"]       # filled as the step's buckets launch; complete between steps
 
