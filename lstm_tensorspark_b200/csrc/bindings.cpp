@@ -19,7 +19,7 @@ int ts_lstm_pointwise_fwd(const void*, const float*, const float*, void*, float*
 int ts_transpose01_rows(const void*, void*, int, int, long long, cudaStream_t);
 int ts_lstm_seq_cluster_probe(int);
 int ts_transpose2d_b16(const void*, void*, int, int, cudaStream_t);
-int ts_colsum_bf16(const void*, float*, void*, int, int, cudaStream_t);
+int ts_colsum_bf16(const void*, float*, void*, int, int, int, int, int, cudaStream_t);
 long long ts_colsum_scratch_bytes(int, int);
 int ts_lstm_pointwise_bwd(const void*, const float*, const float*, const void*, const float*, const float*, void*,
                           float*, int, int, int, cudaStream_t);
@@ -36,6 +36,7 @@ int ts_fused_allreduce(const unsigned long long*, unsigned long long, unsigned l
 int ts_ar_bump_step(int*, cudaStream_t);
 int ts_ar_max_blocks();
 int ts_ar_flag_words();
+int ts_ar_slots();
 int ts_head_fwd_tc(const void*, int, const float*, const float*, const long long*, float*, float*, float*, int*, int, int, int, cudaStream_t);
 int ts_head_logits_generic(const void*, const float*, const float*, float*, int, int, int, int, cudaStream_t);
 int ts_head_bwd(const void*, const float*, const float*, const float*, void*, float*, float*, int, int, int, int, int, cudaStream_t);
@@ -111,19 +112,22 @@ Tensor colsum_bf16(const Tensor& x) {
   chk_cuda(x, "x");
   TORCH_CHECK(x.dim() == 2 && x.is_contiguous() && is_bf16(x) && x.size(1) % 256 == 0, "colsum_bf16: contiguous bf16 [rows, cols], cols % 256 == 0");
   c10::cuda::CUDAGuard g(x.device());
-  auto out = torch::zeros({x.size(1)}, x.options().dtype(torch::kFloat32));
-  check(ts_colsum_bf16(x.data_ptr(), out.data_ptr<float>(), colsum_scratch(x), (int)x.size(0), (int)x.size(1), stream()), "colsum_bf16");
+  auto out = torch::empty({x.size(1)}, x.options().dtype(torch::kFloat32));
+  check(ts_colsum_bf16(x.data_ptr(), out.data_ptr<float>(), colsum_scratch(x), (int)x.size(0), (int)x.size(1), (int)x.size(1), 0, 0, stream()), "colsum_bf16");
   return out;
 }
 
-// column sums accumulated into an existing fp32 [cols] tensor (zero_first: overwrite instead of accumulate)
-void colsum_bf16_into(const Tensor& x, Tensor out, bool zero_first) {
+// column sums written (overwrite) or accumulated into an existing fp32 [cols] tensor; pdl: launch as a programmatic dependent of
+// the previous kernel of the stream (a weight-gradient GEMM that reads the same matrix and leaves SMs idle)
+void colsum_bf16_into(const Tensor& x, Tensor out, bool overwrite, bool pdl, int64_t col0, int64_t ncols) {
   chk_cuda(x, "x"); chk_cuda(out, "out");
   TORCH_CHECK(x.dim() == 2 && is_bf16(x) && x.size(1) % 256 == 0 && out.scalar_type() == torch::kFloat32 && out.numel() == x.size(1),
               "colsum_bf16_into: bf16 [rows, cols % 256 == 0] -> fp32 [cols]");
+  if (ncols <= 0) { col0 = 0; ncols = x.size(1); }
+  TORCH_CHECK(col0 % 256 == 0 && ncols % 256 == 0 && col0 + ncols <= x.size(1), "colsum_bf16_into: 256-aligned column range");
   c10::cuda::CUDAGuard g(x.device());
-  if (zero_first) C10_CUDA_CHECK(cudaMemsetAsync(out.data_ptr(), 0, sizeof(float) * out.numel(), stream()));
-  check(ts_colsum_bf16(x.data_ptr(), out.data_ptr<float>(), colsum_scratch(x), (int)x.size(0), (int)x.size(1), stream()), "colsum_bf16_into");
+  check(ts_colsum_bf16((const char*)x.data_ptr() + 2 * col0, out.data_ptr<float>() + col0, colsum_scratch(x), (int)x.size(0), (int)ncols,
+                       (int)x.size(1), overwrite ? 0 : 1, pdl ? 1 : 0, stream()), "colsum_bf16_into");
 }
 
 // ---- generic LSTM cell epilogue -------------------------------------------------------------------------
@@ -433,7 +437,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("transpose01", &transpose01);
   m.def("transpose2d", &transpose2d);
   m.def("colsum_bf16", &colsum_bf16);
-  m.def("colsum_bf16_into", &colsum_bf16_into);
+  m.def("colsum_bf16_into", &colsum_bf16_into, py::arg("x"), py::arg("out"), py::arg("overwrite"), py::arg("pdl") = false,
+        py::arg("col0") = 0, py::arg("ncols") = 0);
   m.def("lstm_seq_cluster_probe", [](int64_t c) { return ts_lstm_seq_cluster_probe((int)c); });
   m.def("lstm_pointwise_bwd", &lstm_pointwise_bwd);
   m.def("head_xent", &head_xent);
@@ -459,6 +464,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   });
   m.def("ar_max_blocks", []() { return ts_ar_max_blocks(); });
   m.def("ar_flag_words", []() { return ts_ar_flag_words(); });
+  m.def("ar_slots", []() { return ts_ar_slots(); });
   m.def("gemm_generic", &gemm_generic, py::arg("A"), py::arg("B"), py::arg("bias") = py::none(), py::arg("out") = py::none(),
         py::arg("out_fp32") = false, py::arg("beta") = 0.0);
   m.def("gemm2", &gemm2, py::arg("A"), py::arg("B"), py::arg("bias") = py::none(), py::arg("out") = py::none(), py::arg("a_mn") = false,

@@ -150,6 +150,7 @@ __global__ void ar_inc_step_kernel(int* step) { *step += 1; }
 
 template <int kMode, bool kMulticast>
 __global__ void __launch_bounds__(kThreads) ar_two_shot_kernel(const __grid_constant__ ARArgs a) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // the next bucket may start next to this one
   const float lr = kMode == MODE_ADAM ? effective_lr(a) : a.lr;
   uint32_t epoch = a.epochs[blockIdx.x];
   cross_rank_barrier(a, ++epoch);              // every rank's inputs are final
@@ -198,6 +199,7 @@ __global__ void __launch_bounds__(kThreads) ar_two_shot_kernel(const __grid_cons
 // ---------------------------------------------------------------------------------------------------------
 template <int kMode>
 __global__ void __launch_bounds__(kThreads) ar_one_shot_kernel(const __grid_constant__ ARArgs a) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const float lr = kMode == MODE_ADAM ? effective_lr(a) : a.lr;
   uint32_t epoch = a.epochs[blockIdx.x];
   long long stride = (long long)gridDim.x * kThreads;
@@ -298,4 +300,8 @@ extern "C" int ts_ar_bump_step(int* step_dev, cudaStream_t st) {
 }
 
 extern "C" int ts_ar_max_blocks() { return kMaxBlocks; }
-extern "C" int ts_ar_flag_words() { return kMaxBlocks * kMaxRanks; }
+// Flag pads / epoch counters come in kSlots independent sets: two buckets whose kernels are in flight at the same time (the
+// second one is a programmatic dependent of the first) must not share barrier state.
+constexpr int kSlots = 8;
+extern "C" int ts_ar_flag_words() { return kMaxBlocks * kMaxRanks * kSlots; }
+extern "C" int ts_ar_slots() { return kSlots; }

@@ -25,6 +25,7 @@ constexpr int HM = 128;      // rows per CTA
 constexpr int HK = 64;       // k-block
 constexpr int kHStages = 4;
 constexpr int kHThreads = 192;      // warp 0 producer, warp 1 MMA issuer + TMEM allocator, warps 2..5 epilogue
+constexpr int kHBwdJ = 32;          // backward: hidden columns per block (x 4 row groups = 128 threads)
 
 struct HeadParams {
   const float* W;            // [H, C] fp32
@@ -65,13 +66,16 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const HeadParams 
   }
   if (warp == 1) { tc::tmem_alloc(tmem_slot, tmem_cols); tc::tmem_relinquish(); }
   for (int c = threadIdx.x; c < p.NP; c += kHThreads) bias_s[c] = c < p.C ? p.bias[c] : 0.f;
-  // weight image: element (n = class, k) -> block k/64, row n, 16 B chunk ((k%64)/8) ^ (n&7), 2 B slot k%8.  Threads walk k
-  // fastest over classes so the fp32 reads of W[k][0..C) are contiguous per k.
+  // weight image: element (n = class, k) -> block k/64, row n, 16 B chunk ((k%64)/8) ^ (n&7), 2 B slot k%8.  First zero the
+  // image (padding rows C..NP and a ragged last k-block), then walk W [H, C] linearly: coalesced fp32 reads, one bf16 store each.
   {
-    const int total = num_kb * HK * p.NP;
+    const int img16 = (num_kb * wblk) >> 4;
+    for (int i = threadIdx.x; i < img16; i += kHThreads) reinterpret_cast<uint4*>(smem_w)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    const int total = p.H * p.C;
     for (int i = threadIdx.x; i < total; i += kHThreads) {
-      const int n = i % p.NP, k = i / p.NP;
-      float w = (n < p.C && k < p.H) ? p.W[(size_t)k * p.C + n] : 0.f;
+      const int k = i / p.C, n = i - k * p.C;
+      const float w = p.W[i];
       const int kb = k / HK, kk = k % HK;
       const uint32_t off = (uint32_t)kb * wblk + (uint32_t)n * 128 + (uint32_t)((((kk >> 3) ^ (n & 7)) << 4) + ((kk & 7) << 1));
       *reinterpret_cast<__nv_bfloat16*>(smem_w + off) = __float2bfloat16_rn(w);
@@ -172,17 +176,20 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const HeadParams 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// backward: block (jb, bb) = 128 hidden columns x a slab of batch rows.  Thread j keeps W[j, 0:C) and its dW[j, 0:C)
-// partial in registers; per batch row: dh[b, j] = sum_c d[b,c] W[j,c] (written once), dW[j,c] += h[b,j] d[b,c].
-// The dlogits slab sits in shared memory (broadcast reads).  dW / db partials are combined with fp32 atomics
-// (grid.y of them per element) unless the launch is a single slab.
+// backward: block (jb, bb) = 32 hidden columns x a slab of batch rows, 4 row groups per column.  A thread keeps W[j, 0:C) and
+// its dW[j, 0:C) partial in registers; per batch row: dh[b, j] = sum_c d[b,c] W[j,c] (written once), dW[j,c] += h[b,j] d[b,c].
+// The dlogits slab sits in shared memory (broadcast reads).  One slab (the common case) is deterministic: no atomics.
 // ---------------------------------------------------------------------------------------------------------------------
 template <typename T, int CP, typename TDH>
 __global__ void __launch_bounds__(128) head_bwd_kernel(const T* __restrict__ h, const float* __restrict__ W, const float* __restrict__ dlogits,
                                                        const float* __restrict__ dloss, TDH* __restrict__ dh, float* __restrict__ dW,
                                                        float* __restrict__ db, int B, int H, int C, int rows_per_block, int accumulate) {
-  extern __shared__ float ds[];                         // [rows_per_block][CP]
-  const int j = blockIdx.x * 128 + threadIdx.x;
+  // thread = (hidden column j, row group q of 4): lanes 0..31 of a warp = 32 consecutive j (coalesced h / dh accesses), warp = q.
+  // Row b of the slab is handled by group b % 4; the four partial dW rows are added in fixed order through shared memory.
+  extern __shared__ float ds[];                         // [rows_per_block][CP] dlogits slab, then [4][kHBwdJ][CP] partials
+  float* part = ds + (size_t)rows_per_block * CP;
+  const int jl = threadIdx.x & 31, q = threadIdx.x >> 5;
+  const int j = blockIdx.x * kHBwdJ + jl;
   const int b0 = blockIdx.y * rows_per_block;
   const int nb = min(rows_per_block, B - b0);
   const float scale = dloss ? *dloss : 1.f;
@@ -195,7 +202,7 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const T* __restrict__ h, 
 #pragma unroll
   for (int c = 0; c < CP; ++c) { w[c] = (j < H && c < C) ? W[(size_t)j * C + c] : 0.f; acc[c] = 0.f; }
   if (j < H) {
-    for (int b = 0; b < nb; ++b) {
+    for (int b = q; b < nb; b += 4) {
       const float hv = ts::Cvt<T>::to_f(h[(size_t)(b0 + b) * H + j]);
       const float* d = ds + b * CP;
       float s = 0.f;
@@ -203,15 +210,24 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const T* __restrict__ h, 
       for (int c = 0; c < CP; ++c) { s = fmaf(d[c], w[c], s); acc[c] = fmaf(hv, d[c], acc[c]); }
       dh[(size_t)(b0 + b) * H + j] = ts::Cvt<TDH>::from_f(s);
     }
-    const bool atomic = gridDim.y > 1 || accumulate;
+  }
 #pragma unroll
-    for (int c = 0; c < CP; ++c)
-      if (c < C) { if (atomic) atomicAdd(dW + (size_t)j * C + c, acc[c]); else dW[(size_t)j * C + c] = acc[c]; }
+  for (int c = 0; c < CP; ++c) part[(q * kHBwdJ + jl) * CP + c] = acc[c];
+  __syncthreads();
+  const bool atomic = gridDim.y > 1 || accumulate;
+  for (int i = threadIdx.x; i < kHBwdJ * CP; i += 128) {            // fixed-order sum of the four row groups
+    const int jj = i / CP, c = i % CP;
+    const int jg = blockIdx.x * kHBwdJ + jj;
+    if (jg < H && c < C) {
+      const float t = ((part[(0 * kHBwdJ + jj) * CP + c] + part[(1 * kHBwdJ + jj) * CP + c]) + part[(2 * kHBwdJ + jj) * CP + c]) +
+                      part[(3 * kHBwdJ + jj) * CP + c];
+      if (atomic) atomicAdd(dW + (size_t)jg * C + c, t); else dW[(size_t)jg * C + c] = t;
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x < C) {
     float s = 0.f;
     for (int b = 0; b < nb; ++b) s += ds[b * CP + threadIdx.x];
-    if (gridDim.y > 1 || accumulate) atomicAdd(db + threadIdx.x, s); else db[threadIdx.x] = s;
+    if (atomic) atomicAdd(db + threadIdx.x, s); else db[threadIdx.x] = s;
   }
 }
 
@@ -267,13 +283,13 @@ int launch_bwd(const void* h, const float* W, const float* dlogits, const float*
   }
   // one slab (no atomics: deterministic) while the dlogits slab fits in shared memory, 32-row slabs + fp32 atomics beyond
   const int cp = C <= 8 ? 8 : (C <= 16 ? 16 : 32);
-  const int rows = (size_t)B * cp * sizeof(float) <= 40 * 1024 ? B : 32;
-  dim3 grid((H + 127) / 128, (B + rows - 1) / rows);
+  const int rows = (size_t)(B + 4 * kHBwdJ) * cp * sizeof(float) <= 48 * 1024 ? B : 32;
+  dim3 grid((H + kHBwdJ - 1) / kHBwdJ, (B + rows - 1) / rows);
   if (grid.y > 1 && !accumulate) {
     cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)H * C, st);
     cudaMemsetAsync(db, 0, sizeof(float) * (size_t)C, st);
   }
-#define HEAD_BWD(CP) head_bwd_kernel<T, CP, TDH><<<grid, 128, rows * CP * sizeof(float), st>>>((const T*)h, W, dlogits, dloss, (TDH*)dh, dW, db, B, H, C, rows, accumulate)
+#define HEAD_BWD(CP) head_bwd_kernel<T, CP, TDH><<<grid, 128, (rows + 4 * kHBwdJ) * CP * sizeof(float), st>>>((const T*)h, W, dlogits, dloss, (TDH*)dh, dW, db, B, H, C, rows, accumulate)
   if (C <= 8) HEAD_BWD(8); else if (C <= 16) HEAD_BWD(16); else HEAD_BWD(32);
 #undef HEAD_BWD
   return (int)cudaGetLastError();

@@ -158,12 +158,14 @@ extern "C" int ts_transpose2d_b16(const void* src, void* dst, int R, int C, cuda
 // counter per column block) adds the slabs in fixed order and accumulates the result into out (beta = 1).
 namespace {
 __global__ void colsum_bf16_kernel(const uint4* __restrict__ src, float* __restrict__ out, float* __restrict__ partial,
-                                   unsigned int* __restrict__ tickets, int rows, int cols, int rows_per_block) {
+                                   unsigned int* __restrict__ tickets, int rows, int cols, int rows_per_block, int accumulate, int pdl,
+                                   int pitch_cols) {
   __shared__ float red[8][256];
   __shared__ unsigned int ticket_s;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cv = blockIdx.x * 32 + lane;                       // 16 B column-vector index (8 columns)
-  const int vec_per_row = cols / 8;
+  const int vec_per_row = pitch_cols / 8;                      // (src / out already point at the first column of this launch)
   const int r_begin = blockIdx.y * rows_per_block;
   const int r_end = min(rows, r_begin + rows_per_block);
   float acc[8];
@@ -185,18 +187,25 @@ __global__ void colsum_bf16_kernel(const uint4* __restrict__ src, float* __restr
 #pragma unroll
   for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
   const int col = blockIdx.x * 256 + threadIdx.x;
-  if (gridDim.y == 1) { out[col] += s; return; }
-  partial[(size_t)blockIdx.y * cols + col] = s;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) ticket_s = atomicAdd(tickets + blockIdx.x, 1u);
-  __syncthreads();
-  if (ticket_s != gridDim.y - 1) return;
-  __threadfence();
-  float t = 0.f;
-  for (unsigned int y = 0; y < gridDim.y; ++y) t += __ldcg(partial + (size_t)y * cols + col);     // fixed order
-  out[col] += t;
-  if (threadIdx.x == 0) tickets[blockIdx.x] = 0u;              // ready for the next launch
+  if (gridDim.y == 1) {
+    out[col] = accumulate ? out[col] + s : s;
+  } else {
+    partial[(size_t)blockIdx.y * cols + col] = s;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) ticket_s = atomicAdd(tickets + blockIdx.x, 1u);
+    __syncthreads();
+    if (ticket_s == gridDim.y - 1) {
+      __threadfence();
+      float t = 0.f;
+      for (unsigned int y = 0; y < gridDim.y; ++y) t += __ldcg(partial + (size_t)y * cols + col);     // fixed order
+      out[col] = accumulate ? out[col] + t : t;
+      if (threadIdx.x == 0) tickets[blockIdx.x] = 0u;            // ready for the next launch
+    }
+  }
+  // launched as a programmatic dependent of a weight-gradient GEMM (it runs on the SMs that GEMM leaves idle and reads the same
+  // dG): do not let anything behind us start before that GEMM has completed
+  if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 }  // namespace
 
@@ -209,12 +218,20 @@ extern "C" long long ts_colsum_scratch_bytes(int rows, int cols) {
   return (long long)kColsumTickets * 4 + slabs * cols * 4;
 }
 
-extern "C" int ts_colsum_bf16(const void* src, float* out, void* scratch, int rows, int cols, cudaStream_t st) {
+// cols = columns summed by this launch (a 256-aligned sub-range of a matrix with row pitch pitch_cols; src / out point at its first column)
+extern "C" int ts_colsum_bf16(const void* src, float* out, void* scratch, int rows, int cols, int pitch_cols, int accumulate, int pdl,
+                              cudaStream_t st) {
   if (cols % 256 != 0 || cols / 256 > kColsumTickets) return -2;
   const int rows_per_block = 512;
   dim3 grid(cols / 256, (rows + rows_per_block - 1) / rows_per_block);
   unsigned int* tickets = (unsigned int*)scratch;
   float* partial = (float*)((char*)scratch + (size_t)kColsumTickets * 4);
-  colsum_bf16_kernel<<<grid, 256, 0, st>>>((const uint4*)src, out, partial, tickets, rows, cols, rows_per_block);
-  return (int)cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return (int)cudaLaunchKernelEx(&cfg, colsum_bf16_kernel, (const uint4*)src, out, partial, tickets, rows, cols, rows_per_block, accumulate, pdl,
+                                 pitch_cols);
 }

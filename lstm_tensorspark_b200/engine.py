@@ -117,7 +117,7 @@ class TrainEngine:
                 b = plan[state["next"]]
                 if b["need"] is None or (b["need"] & flat._stale):
                     break
-                cuda_lstm.AFTER_SEQ_BWD.append(lambda b=b: comm.launch_bucket(b["lo"], b["hi"], pdl=_BUCKET_PDL, blocks=self.cfg.grad_bucket_blocks))
+                cuda_lstm.queue_after_big_launch(lambda b=b: comm.launch_bucket(b["lo"], b["hi"], pdl=_BUCKET_PDL, blocks=self.cfg.grad_bucket_blocks))
                 state["next"] += 1
 
         cuda_lstm.HOOKS["grads_written"] = ready
@@ -126,8 +126,7 @@ class TrainEngine:
         finally:
             cuda_lstm.HOOKS["grads_written"] = None
         flat.finalize_grads()
-        while cuda_lstm.AFTER_SEQ_BWD:                      # queued but no lower recurrence followed (generic path)
-            cuda_lstm.AFTER_SEQ_BWD.pop(0)()
+        cuda_lstm._after_big_launch(flush=True)             # queued, but no big kernel followed (generic path / last layer)
         for b in plan[state["next"]:]:
             comm.launch_bucket(b["lo"], b["hi"])
 
@@ -136,6 +135,10 @@ class TrainEngine:
         loss, _logits, _correct = self.model(x, y)
         if self._wd_autograd:
             loss = loss + torch.stack([fn(v) * wd for (v, fn, wd) in self._wd_autograd]).sum()
+        l2 = None
+        if self._wd_in_kernel:                 # reported total loss includes the L2 value (of the weights this step used); its
+            with torch.no_grad():              # gradient is applied by the update kernel
+                l2 = torch.stack([fn(v) * wd for (v, fn, wd) in self._wd_in_kernel]).sum()
         if self._bucket_plan:
             self._backward_with_buckets(loss)      # backward + per-bucket fused allreduce / update, overlapped with backward
         else:
@@ -145,9 +148,8 @@ class TrainEngine:
                 self.comm.grad_step_(self.flat, self.optimizer)
             else:
                 self.optimizer.step()
-        if self._wd_in_kernel:                 # reported total loss includes the L2 value; its gradient is applied by the update kernel
-            with torch.no_grad():
-                loss = loss.detach() + torch.stack([fn(v) * wd for (v, fn, wd) in self._wd_in_kernel]).sum()
+        if l2 is not None:
+            loss = loss.detach() + l2
         return loss.detach()
 
     def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:

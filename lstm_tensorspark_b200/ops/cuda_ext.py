@@ -10,7 +10,7 @@ import os
 _EXT = None
 _ERR = None
 LAUNCHES = {"n": 0}          # number of OUR kernels launched through the extension (bench.py "gpu_launches")
-_NO_KERNEL = {"ar_max_blocks", "ar_flag_words"}
+_NO_KERNEL = {"ar_max_blocks", "ar_flag_words", "ar_slots"}
 
 
 class _Counting:

@@ -36,12 +36,25 @@ STATS = {"fast_fwd": 0, "fast_bwd": 0, "generic_fwd": 0, "generic_bwd": 0, "tc_g
 # launch a finished bucket's fused allreduce + update as a programmatic dependent, so it runs NEXT TO that kernel (on the SMs
 # the recurrence leaves idle / co-resident with the GEMM's CTAs) instead of after it.
 HOOKS = {"grads_written": None}
-AFTER_SEQ_BWD = []
+AFTER_SEQ_BWD = []          # [(generation when queued, closure)]
+_GEN = {"n": 0}
 
 
-def _after_big_launch():
-    while AFTER_SEQ_BWD:
-        AFTER_SEQ_BWD.pop(0)()
+def queue_after_big_launch(fn):
+    AFTER_SEQ_BWD.append((_GEN["n"], fn))
+
+
+def _big_launch_begin():
+    """A big backward kernel (recurrence / weight-gradient GEMM) is about to be launched as an ORDINARY launch: everything
+    enqueued before it is complete when it starts."""
+    _GEN["n"] += 1
+
+
+def _after_big_launch(flush: bool = False):
+    """Launch the queued bucket closures as programmatic dependents of the kernel just launched - but only those queued
+    BEFORE that kernel was launched: a dependent may start while its primary runs, so its inputs must not come from it."""
+    while AFTER_SEQ_BWD and (flush or AFTER_SEQ_BWD[0][0] < _GEN["n"]):
+        AFTER_SEQ_BWD.pop(0)[1]()
 
 
 def _grads_written():
@@ -97,6 +110,7 @@ def _accumulate_grad(w_addr: int, a_t: torch.Tensor, b: torch.Tensor):
     view (overwrite on the first write of a step, accumulate afterwards) and None is returned to autograd."""
     sink = grad_sink(w_addr)
     if sink is not None:
+        _big_launch_begin()
         G.matmul(a_t, b.t(), out=sink[0], accumulate=sink[1])
         _after_big_launch()                  # finished buckets of earlier gradients: allreduce them under this GEMM
         _grads_written()
@@ -104,14 +118,41 @@ def _accumulate_grad(w_addr: int, a_t: torch.Tensor, b: torch.Tensor):
     return G.matmul(a_t, b.t(), out_dtype=torch.float32)
 
 
-def _bias_grad(b_addr: int, dg2d: torch.Tensor):
-    """db = column sums of dG; straight into the flat grad view when there is one."""
+_BIAS_SPLIT = {}
+
+
+def _bias_grad(b_addr: int, dg2d: torch.Tensor, under_gemm: bool = False, part: int = -1):
+    """db = column sums of dG; straight into the flat grad view when there is one.  ``under_gemm``: the previous launch of the
+    stream is a weight-gradient GEMM over the same dG that leaves SMs idle - run next to it (programmatic dependent launch).
+    ``part`` 0 / 1: only the first / second half of the columns (one half under each of the layer's two weight-gradient GEMMs:
+    on the ~20 idle SMs a half takes about as long as the GEMM it hides under); the value for autograd comes from part 1."""
+    fast = dg2d.is_cuda and dg2d.dtype == torch.bfloat16 and dg2d.shape[1] % 512 == 0 and dg2d.is_contiguous()
+    if part == 0:
+        if not fast:
+            return None                                   # everything happens with the part-1 call
+        sink = grad_sink(b_addr)
+        _BIAS_SPLIT[b_addr] = sink
+        if sink is None:
+            return None
+        half = dg2d.shape[1] // 2
+        STATS["kernels"] += 1
+        ext().colsum_bf16_into(dg2d, sink[0], not sink[1], under_gemm, 0, half)
+        return None
+    if part == 1 and fast and b_addr in _BIAS_SPLIT:
+        sink = _BIAS_SPLIT.pop(b_addr)
+        if sink is not None:
+            half = dg2d.shape[1] // 2
+            STATS["kernels"] += 1
+            ext().colsum_bf16_into(dg2d, sink[0], not sink[1], under_gemm, half, half)
+            _grads_written()
+            return None
+        return ext().colsum_bf16(dg2d)
     fast = dg2d.is_cuda and dg2d.dtype == torch.bfloat16 and dg2d.shape[1] % 256 == 0 and dg2d.is_contiguous()
     sink = grad_sink(b_addr)
     if fast:
         STATS["kernels"] += 1
         if sink is not None:
-            ext().colsum_bf16_into(dg2d, sink[0], not sink[1])
+            ext().colsum_bf16_into(dg2d, sink[0], not sink[1], under_gemm and part < 0)
             _grads_written()
             return None
         return ext().colsum_bf16(dg2d)
@@ -275,6 +316,7 @@ class _LSTMSeqFn(torch.autograd.Function):
         dhT = (dh_T.float().contiguous() if dh_T is not None else torch.zeros(B, H, dtype=torch.float32, device=dev))
         if ctx.fast:
             w_hT = _transposed(w_h_c)
+            _big_launch_begin()
             dpre, dh0, dc0 = E.lstm_seq_bwd(dh_seq, w_hT, act, c_seq, dhT, dcT, _sync_ws(dev), SEQ_VARIANT)
             STATS["fast_bwd"] += 1
             STATS["kernels"] += 1
@@ -465,13 +507,18 @@ class _LSTMPairFn(torch.autograd.Function):
         STATS["kernels"] += 5
         a = ctx.addrs
         dg_b = dpre_b.view(T * B, 4 * Hb)
+        # the bias column sums run NEXT TO the first weight-gradient GEMM of their layer (same dG, idle SMs), not after it
+        # (each GEMM is followed by: finished gradient buckets [programmatic dependents of the GEMM], then half of the layer's
+        # bias column sums [programmatic dependent of whatever was launched last] - all three run side by side)
         dw_xb = _accumulate_grad(a[3], dg_b.t(), h_seq_a[1:].reshape(T * B, Ha))
+        _bias_grad(a[5], dg_b, under_gemm=dw_xb is None, part=0)
         dw_hb = _accumulate_grad(a[4], dg_b.t(), h_seq_b[:T].reshape(T * B, Hb))
-        db_b = _bias_grad(a[5], dg_b)
+        db_b = _bias_grad(a[5], dg_b, under_gemm=dw_hb is None, part=1)
         dg_a = dpre_a.view(T * B, 4 * Ha)
         dw_xa = _accumulate_grad(a[0], dg_a.t(), x2d)
+        _bias_grad(a[2], dg_a, under_gemm=dw_xa is None, part=0)
         dw_ha = _accumulate_grad(a[1], dg_a.t(), h_seq_a[:T].reshape(T * B, Ha))
-        db_a = _bias_grad(a[2], dg_a)
+        db_a = _bias_grad(a[2], dg_a, under_gemm=dw_ha is None, part=1)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = G.matmul(dg_a, wxa.t(), out_dtype=cd).view(T, B, D)

@@ -103,7 +103,8 @@ class FusedComm(TorchDistComm):
         had_shadow = flat.shadow is not None
         flat.shadow = self.shadow
         flat.refresh_shadow()
-        self.epochs = torch.zeros(E.ar_max_blocks(), dtype=torch.int32, device=self.device)
+        self.slots = E.ar_slots()
+        self.epochs = torch.zeros(E.ar_max_blocks() * self.slots, dtype=torch.int32, device=self.device)
         self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.flat = flat
         torch.cuda.synchronize(self.device)
@@ -122,7 +123,7 @@ class FusedComm(TorchDistComm):
 
     def _launch(self, mode: int, off_in: int, n: int, lr: float = 0.0, b1: float = 0.0, b2: float = 0.0, eps: float = 0.0,
                 wd: float = 0.0, m=None, v=None, force: Optional[str] = None, step_dev=None, elem_off: int = 0,
-                wd_numel: int = -1, bump_step: bool = True, pdl: bool = False, blocks: int = 0):
+                wd_numel: int = -1, bump_step: bool = True, pdl: bool = False, blocks: int = 0, slot: int = 0):
         """One launch over elements [elem_off, elem_off + n) of the symmetric buffers (a gradient bucket or the whole message)."""
         E = ext()
         A = self.arena
@@ -133,8 +134,11 @@ class FusedComm(TorchDistComm):
         else:
             off_in_eff = off_in
         e4, e2 = 4 * elem_off, 2 * elem_off
+        mb = E.ar_max_blocks()
+        slot = slot % self.slots                       # independent barrier state per slot (kernels of two buckets may overlap)
+        fl = 4 * slot * (E.ar_flag_words() // self.slots)
         rows = [[p + e4 for p in A.peers(off_in_eff)], [p + e4 for p in A.peers(self.off_data)],
-                [p + e2 for p in A.peers(self.off_shadow)], A.peers(self.off_flags)]
+                [p + e2 for p in A.peers(self.off_shadow)], [p + fl for p in A.peers(self.off_flags)]]
         ptrs = torch.tensor(rows, dtype=torch.int64)
         if m is not None and elem_off:
             m, v = m[elem_off:elem_off + n], v[elem_off:elem_off + n]
@@ -144,7 +148,7 @@ class FusedComm(TorchDistComm):
             wd_numel = max(0, min(n, wd_numel - elem_off))
         nblk = blocks or self.blocks_override or (AR_BLOCKS_LARGE if 4 * n >= (32 << 20) else AR_BLOCKS)
         E.fused_allreduce(ptrs, (A.mc(off_in_eff) + e4) if mc else 0, (A.mc(self.off_data) + e4) if mc else 0,
-                          (A.mc(self.off_shadow) + e2) if mc else 0, m, v, self.epochs, self.err, n, self.rank, self.world_size,
+                          (A.mc(self.off_shadow) + e2) if mc else 0, m, v, self.epochs[slot * mb:(slot + 1) * mb], self.err, n, self.rank, self.world_size,
                           mode, two_shot, mc, nblk, lr, b1, b2, eps, wd, float(self.timeout_s), step_dev, wd_numel, bump_step, pdl)
         self.launches += 1
         return two_shot
@@ -176,10 +180,10 @@ class FusedComm(TorchDistComm):
         if opt.kind == "adam":
             two = self._launch(MODE_ADAM, self.off_grad, n, opt.lr, opt.beta1, opt.beta2, opt.eps, opt.weight_decay, opt.m, opt.v,
                                force=force, step_dev=opt.step_dev, elem_off=lo, wd_numel=opt.wd_numel, bump_step=gs["bump"],
-                               pdl=pdl, blocks=blocks)
+                               pdl=pdl, blocks=blocks, slot=len(gs["buckets"]))
         else:
             two = self._launch(MODE_SGD, self.off_grad, n, opt.lr, wd=opt.weight_decay, force=force, elem_off=lo,
-                               wd_numel=opt.wd_numel, pdl=pdl, blocks=blocks)
+                               wd_numel=opt.wd_numel, pdl=pdl, blocks=blocks, slot=len(gs["buckets"]))
         gs["bump"] = False
         gs["buckets"].append((lo, hi, bool(two)))
 

@@ -24,7 +24,7 @@ def test_extension_is_built_and_importable():
         g.build()
     from lstm_tensorspark_b200.ops.cuda_ext import ext
     E = ext()
-    assert E.ar_flag_words() == E.ar_max_blocks() * 16
+    assert E.ar_flag_words() == E.ar_max_blocks() * 16 * E.ar_slots()
     for name in ("gemm2", "gemm_generic", "lstm_seq_fwd", "lstm_seq_bwd", "fused_allreduce", "head_fwd", "head_bwd", "flat_adam", "lstm_pointwise_fwd"):
         assert hasattr(E._m, name)
 
