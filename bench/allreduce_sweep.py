@@ -55,10 +55,10 @@ def main():
     nccl_buf = torch.zeros(max_bytes // 4, device=dev)
     while size <= max_bytes:
         n = size // 4
-        n = max(4096 // 4, (n + 3) // 4 * 4)
+        n = max(1024 // 4, (n + 3) // 4 * 4)
         iters = 200 if size <= (1 << 20) else (50 if size <= (1 << 26) else 10)
         rec = {"bytes": n * 4, "world": world}
-        variants = [("one_shot", "one_shot", "0", 0, False), ("two_shot_p2p", "two_shot", "0", 0, False)]
+        variants = [("auto", None, "auto", 0, False), ("one_shot", "one_shot", "0", 0, False), ("two_shot_p2p", "two_shot", "0", 0, False)]
         if comm.arena.mc_base:
             variants.append(("two_shot_nvls", "two_shot", "auto", 0, False))
             if tune and size >= (1 << 22):

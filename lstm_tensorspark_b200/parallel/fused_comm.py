@@ -22,7 +22,7 @@ from ..ops.cuda_ext import ext
 from .comm import TorchDistComm
 
 MODE_AVG, MODE_SGD, MODE_ADAM = 0, 1, 2
-TWO_SHOT_BYTES = int(os.environ.get("LSTM_TS_AR_TWO_SHOT_BYTES", str(32 * 1024)))     # measured: two-shot wins from ~16 KB up (profiles/)
+TWO_SHOT_BYTES = int(os.environ.get("LSTM_TS_AR_TWO_SHOT_BYTES", str(8 * 1024)))      # measured at 8 GPUs (profiles/logs/sweep8_r2.log): two-shot wins from 16 KB up, ties below
 AR_BLOCKS = int(os.environ.get("LSTM_TS_AR_BLOCKS", "64"))
 AR_BLOCKS_LARGE = int(os.environ.get("LSTM_TS_AR_BLOCKS_LARGE", "64"))    # messages >= 32 MB (measured: 64 = 128 = 256 blocks, unroll irrelevant: sweep8c.log)
 
