@@ -70,7 +70,7 @@ def check_simple():
     W = torch.randn(H, C, device=dev) * 0.1
     b = torch.randn(C, device=dev)
     y = torch.randint(0, C, (B,), device=dev)
-    logits, dlog, loss, corr = E.head_xent(hh, W, b, y)
+    logits, dlog, loss, corr = E.head_fwd(hh, W, b, y)
     lr, lossr, corrr = ref.head_xent(hh, W, b, y)
     _emit("head_xent", logit_err=float((logits - lr).abs().max()), loss=float(loss / B), loss_ref=float(lossr), correct=int(corr), correct_ref=int(corrr))
     # adam

@@ -144,8 +144,14 @@ def dump_sass(out_dir: str) -> List[str]:
 
 
 # lstm_seq_tcgen05.cu has ~30 template instantiations (ring depths, tuning variants): the committed listing keeps the
-# ones that run by default (forward K-split 5-stage, backward 5-stage, streamed-weights 8-stage, prologue).
-SASS_KEEP = {"lstm_seq_tcgen05.cu": ("ILb0ELi5ELi1ELb0ELb1E", "ILb1ELi5ELi1ELb0ELb0E", "ILb0ELi8ELi1ELb1ELb0E", "seq_prologue_kernel")}
+# ones that run by default (wavefront: forward 6-stage / backward 4-stage with two batch tiles per CTA; single layer: forward
+# K-split 5-stage, backward 5-stage; streamed-weights 8-stage; prologue).
+# gemm2_tcgen05.cu has 48 (cta_group x tile x operand majors x output mode); kept: the 2-CTA x-projection / dX / dW kernels and the
+# single-CTA dataflow-gated ones of the layer wavefront.
+SASS_KEEP = {"lstm_seq_tcgen05.cu": ("ILb0ELi6ELi2ELb0ELb0E", "ILb1ELi4ELi2ELb0ELb0E", "ILb0ELi5ELi1ELb0ELb1E", "ILb1ELi5ELi1ELb0ELb0E",
+                                     "ILb0ELi8ELi1ELb1ELb0E", "seq_prologue_kernel"),
+             "gemm2_tcgen05.cu": ("ILi2ELi256ELb0ELb0ELi0E", "ILi2ELi256ELb0ELb1ELi0E", "ILi2ELi256ELb1ELb1ELi1E", "ILi2ELi256ELb1ELb1ELi2E",
+                                  "ILi1ELi256ELb0ELb0ELi0E", "ILi1ELi256ELb0ELb1ELi0E")}
 
 
 def _filter_sass(text: str, keep) -> str:

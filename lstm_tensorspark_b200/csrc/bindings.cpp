@@ -23,8 +23,6 @@ int ts_colsum_bf16(const void*, float*, void*, int, int, int, int, int, cudaStre
 long long ts_colsum_scratch_bytes(int, int);
 int ts_lstm_pointwise_bwd(const void*, const float*, const float*, const void*, const float*, const float*, void*,
                           float*, int, int, int, cudaStream_t);
-int ts_head_xent(const void*, const float*, const float*, const long long*, float*, float*, float*, int*, int, int, int,
-                 int, cudaStream_t);
 int ts_xent_rows(const float*, const long long*, float*, float*, int*, int, int, cudaStream_t);
 int ts_flat_adam(float*, const float*, float*, float*, void*, long long, float, float, float, float, float, float,
                  cudaStream_t, int*, long long);
@@ -163,22 +161,6 @@ std::vector<Tensor> lstm_pointwise_bwd(const std::optional<Tensor>& dh_a, const 
 }
 
 // ---- head ---------------------------------------------------------------------------------------------------
-std::vector<Tensor> head_xent(const Tensor& h, const Tensor& W, const Tensor& bias, const Tensor& labels) {
-  chk_cuda(h, "h"); chk_cuda(W, "W"); chk_cuda(bias, "bias"); chk_cuda(labels, "labels");
-  c10::cuda::CUDAGuard g(h.device());
-  int B = h.size(0), H = h.size(1), C = W.size(1);
-  TORCH_CHECK(W.size(0) == H && W.scalar_type() == torch::kFloat32 && bias.scalar_type() == torch::kFloat32, "head W/b");
-  TORCH_CHECK(labels.scalar_type() == torch::kInt64 && labels.numel() == B, "labels int64 [B]");
-  auto fo = torch::TensorOptions().device(h.device()).dtype(torch::kFloat32);
-  auto logits = torch::empty({B, C}, fo), dlogits = torch::empty({B, C}, fo);
-  auto loss = torch::zeros({1}, fo);
-  auto correct = torch::zeros({1}, fo.dtype(torch::kInt32));
-  check(ts_head_xent(h.data_ptr(), W.data_ptr<float>(), bias.data_ptr<float>(), (const long long*)labels.data_ptr<int64_t>(),
-                     logits.data_ptr<float>(), dlogits.data_ptr<float>(), loss.data_ptr<float>(), correct.data_ptr<int>(),
-                     B, H, C, is_bf16(h), stream()), "head_xent");
-  return {logits, dlogits, loss, correct};
-}
-
 std::vector<Tensor> xent_rows(const Tensor& logits, const Tensor& labels) {
   chk_cuda(logits, "logits"); chk_cuda(labels, "labels");
   c10::cuda::CUDAGuard g(logits.device());
@@ -441,7 +423,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("col0") = 0, py::arg("ncols") = 0);
   m.def("lstm_seq_cluster_probe", [](int64_t c) { return ts_lstm_seq_cluster_probe((int)c); });
   m.def("lstm_pointwise_bwd", &lstm_pointwise_bwd);
-  m.def("head_xent", &head_xent);
   m.def("xent_rows", &xent_rows);
   m.def("head_fwd", &head_fwd);
   m.def("head_bwd", &head_bwd, py::arg("h"), py::arg("W"), py::arg("dlogits"), py::arg("dloss"), py::arg("dW"), py::arg("db"),
