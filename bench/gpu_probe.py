@@ -408,6 +408,50 @@ def check_seq_tune():
                 _emit("fwd_variant", T=T, B=B, H=H, tiles=tiles, stages=st, error=repr(e)[:300])
 
 
+def check_tiles2_tune():
+    """The two-tiles-per-CTA kernels the layer wavefront launches (64 CTAs per layer), one layer alone: ring depth / sync mode."""
+    import torch
+    from lstm_tensorspark_b200.ops import cuda_lstm
+    from lstm_tensorspark_b200.ops.cuda_ext import ext
+    E = ext()
+    dev = torch.device("cuda")
+    T, B, H = 128, 256, 1024
+    torch.manual_seed(0)
+    gx = (torch.randn(T, B, 4 * H, device=dev) * 0.5).bfloat16()
+    whb = (torch.randn(4 * H, H, device=dev) / H ** 0.5).bfloat16()
+    whT = whb.t().contiguous()
+    bias = torch.zeros(4 * H, device=dev)
+    h0 = torch.zeros(B, H, device=dev).bfloat16(); c0 = torch.zeros(B, H, device=dev)
+    ws = cuda_lstm._sync_ws(dev)
+    hseq, cseq, act = E.lstm_seq_fwd(gx, whb, bias, h0, c0, ws, 2)
+    dh = torch.randn(T, B, H, device=dev).bfloat16()
+    z = torch.zeros(B, H, device=dev)
+    for st in (0, 4, 5, 6):
+        for sync in (0, 1, 2):
+            v = 2 + 16 * st + 65536 * sync
+            try:
+                ms = _time_ms(lambda: E.lstm_seq_fwd(gx, whb, bias, h0, c0, ws, v), iters=5, warm=2)
+                cuda_lstm.check_kernel_errors(dev)
+                _emit("tiles2_fwd", stages=st, sync=sync, us_per_step=ms * 1e3 / T)
+            except Exception as e:        # noqa: BLE001
+                _emit("tiles2_fwd", stages=st, sync=sync, error=repr(e)[:200])
+    for st in (0, 3, 4):
+        for sync in (0, 1, 2):
+            v = 2 + 16 * st + 65536 * sync
+            try:
+                ms = _time_ms(lambda: E.lstm_seq_bwd(dh, whT, act, cseq, z, z, ws, v), iters=5, warm=2)
+                cuda_lstm.check_kernel_errors(dev)
+                _emit("tiles2_bwd", stages=st, sync=sync, us_per_step=ms * 1e3 / (T + 1))
+            except Exception as e:        # noqa: BLE001
+                _emit("tiles2_bwd", stages=st, sync=sync, error=repr(e)[:200])
+    # one tile per CTA on 128 CTAs (the single-layer default), for reference
+    for v, nm in ((0, "ksplit_default"), (524288, "nosplit")):
+        ms = _time_ms(lambda: E.lstm_seq_fwd(gx, whb, bias, h0, c0, ws, v), iters=5, warm=2)
+        _emit("tiles1_fwd", variant=nm, us_per_step=ms * 1e3 / T)
+    ms = _time_ms(lambda: E.lstm_seq_bwd(dh, whT, act, cseq, z, z, ws, 0), iters=5, warm=2)
+    _emit("tiles1_bwd", us_per_step=ms * 1e3 / (T + 1))
+
+
 def check_bwd_tune():
     """Backward kernel: per-phase timestamps of CTA 0 (first operand block ready / accumulator ready / signalled)."""
     import torch
@@ -537,7 +581,7 @@ def check_iris_gpu():
     _emit("iris_gpu_standalone", rc=r.returncode, tail=(r.stdout + r.stderr)[-600:])
 
 
-CHECKS = {"wave": check_wave, "wave_bwd": check_wave_bwd, "gemm2": check_gemm2, "gemm2_dw": check_gemm2_dw, "seq_h2048": check_seq_h2048, "bwd_tune": check_bwd_tune, "skew": check_skew, "seq_tiles": check_seq_tiles, "seq_tune": check_seq_tune, "env": check_env, "simple": check_simple, "generic": check_generic, "seq_small": check_seq_small,
+CHECKS = {"tiles2": check_tiles2_tune, "wave": check_wave, "wave_bwd": check_wave_bwd, "gemm2": check_gemm2, "gemm2_dw": check_gemm2_dw, "seq_h2048": check_seq_h2048, "bwd_tune": check_bwd_tune, "skew": check_skew, "seq_tiles": check_seq_tiles, "seq_tune": check_seq_tune, "env": check_env, "simple": check_simple, "generic": check_generic, "seq_small": check_seq_small,
           "seq_big": check_seq_big, "engine": check_engine, "iris_gpu": check_iris_gpu}
 
 

@@ -718,7 +718,10 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
 #pragma unroll
         for (int tile = 0; tile < kTiles; ++tile) {
           epi_bar();
-          if (etid == 0) signal_counter(p.sync + kSyncKb + ((size_t)(mb0 + tile) * (H / BK) + (in_mb >> 2)) * 32);
+          if (etid == 0) {
+            if (p.sync_mode == 1) signal_counter(p.sync + mb0 + tile);
+            else signal_counter(p.sync + kSyncKb + ((size_t)(mb0 + tile) * (H / BK) + (in_mb >> 2)) * 32);
+          }
         }
       }
     } else {
@@ -826,7 +829,10 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmap_w, const SeqParams p) {
             }
             if (p.extra_signal) {                   // dpre[0] (natural layout, written after the last per-step signal) is visible to the gated GEMM
               epi_bar();
-              if (etid == 0) signal_counter(p.sync + kSyncKb + ((size_t)mb * (4 * H / BK) + in_mb) * 32);
+              if (etid == 0) {
+                if (p.sync_mode == 1) signal_counter(p.sync + mb);
+                else signal_counter(p.sync + kSyncKb + ((size_t)mb * (4 * H / BK) + in_mb) * 32);
+              }
             }
             continue;
           }

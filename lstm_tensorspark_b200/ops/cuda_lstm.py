@@ -431,6 +431,29 @@ def wavefront_supported(x_seq: torch.Tensor, h_a: int, h_b: int) -> bool:
     return h_a // 16 + h_b // 16 + 8 <= _coresident_ctas(x_seq.device) + 16 and h_a // 16 + h_b // 16 + 8 <= _sms(x_seq.device)
 
 
+WAVE_SYNC_MODE = int(os.environ.get("LSTM_TS_WAVE_SYNC", "1"))      # 1: one arrival counter per batch tile (measured 2.5 % faster with two
+                                                                    # tiles per CTA), 0: one per operand k-block (profiles/logs/tiles2_tune.log)
+
+
+def _wave_variant() -> int:
+    return (SEQ_VARIANT & ~(15 | (3 << 16))) | 2 | ((WAVE_SYNC_MODE & 1) << 16)
+
+
+def _gate_off(var: int) -> int:
+    return 0 if (var >> 16) & 3 == 1 else 512
+
+
+def _gate_cfg(var: int, tiles_m: int, nkb: int, per_kb_step: int, ctas_per_tile: int, base_steps: int, step_sign: int, rows: int, bwd: bool):
+    """Gate of the wavefront GEMM on the producer layer's arrival counters: [count, stride, base, per_step, rows_per_step, use_last,
+    reverse_m].  A time step's natural-layout rows are complete with the producer's (step + 1)-th signal, hence base = 2 steps
+    (forward: target(t) = per_step * (t + 2)) or T + 1 (backward: target(t) = per_step * (T + 1 - t))."""
+    if (var >> 16) & 3 == 1:                # one counter per batch tile, every CTA of the tile arrives once per step
+        per = ctas_per_tile
+        return [tiles_m, 1, per * base_steps, per * step_sign, rows, 0 if bwd else 1, 1 if bwd else 0]
+    per = per_kb_step                       # one counter per operand k-block (fwd: 4 producer CTAs, bwd: 1)
+    return [tiles_m * nkb, 32, per * base_steps, per * step_sign, rows, 0 if bwd else 1, 1 if bwd else 0]
+
+
 class _LSTMPairFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_seq, h0a, c0a, w_xa, w_ha, b_a, h0b, c0b, w_xb, w_hb, b_b):
@@ -455,7 +478,7 @@ class _LSTMPairFn(torch.autograd.Function):
         tn = 4 * Hb // 256
         ws_a, ws_b, done = _pair_ws(dev, "fwd", T * tn * 2)
         done.zero_()                                                     # (the prologue kernels zero ws_a / ws_b)
-        var = (SEQ_VARIANT & ~15) | 2                                    # two batch tiles per CTA: 64 CTAs per layer at H = 1024
+        var = _wave_variant()                                            # two batch tiles per CTA: 64 CTAs per layer at H = 1024
         # ONE stream, a programmatic-dependent-launch chain: L_a -> L_b (starts once every CTA of L_a is resident) -> gated GEMM
         # (starts once every CTA of L_b is resident, on the SMs that are left).  The order in which the three grids take their
         # SMs is thereby fixed (a kernel that is still queueing could otherwise starve the chain head of co-resident SMs).
@@ -467,7 +490,8 @@ class _LSTMPairFn(torch.autograd.Function):
         # single-CTA tiles: the recurrences' CTAs are spread one per TPC, the SMs they leave free rarely form CTA pairs
         free_ctas = max(1, _sms(dev) - Ha // 16 - Hb // 16)
         E.gemm2(h_seq_a[1:].view(T * B, Ha), wxb, out=gx_b.view(T * B, 4 * Hb), ctas=1, bn=256, max_ctas=free_ctas,
-                gate=ws_a[512:], gate_cfg=[2 * (Ha // 64), 32, 8, 4, B, 1, 0], done=done, gate_err=ws_a[SYNC_WORDS - 1:], pdl=True)
+                gate=ws_a[_gate_off(var):], gate_cfg=_gate_cfg(var, 2, Ha // 64, 4, 4 * Ha // 64, 2, 1, B, False), done=done,
+                gate_err=ws_a[SYNC_WORDS - 1:], pdl=True)
         STATS["fast_fwd"] += 2
         STATS["kernels"] += 3
         STATS["wavefront_fwd"] = STATS.get("wavefront_fwd", 0) + 1
@@ -496,13 +520,14 @@ class _LSTMPairFn(torch.autograd.Function):
         tn = Ha // 256
         ws_b, ws_a, done = _pair_ws(dev, "bwd", T * tn * 2)               # head of the backward chain is layer b
         ws_a[:SYNC_WORDS - 1].zero_(); ws_b[:SYNC_WORDS - 1].zero_(); done.zero_()
-        var = (SEQ_VARIANT & ~15) | 2
+        var = _wave_variant()
         # programmatic-dependent-launch chain on one stream (see forward): L_b -> L_a -> gated dX GEMM
         E.lstm_seq_bwd_into(dh_seq_b, whT_b, act_b, c_seq_b, dpre_b, dh0b, dc0b, til_b, ws_b, var, None, 0, True, 0, 1)
         E.lstm_seq_bwd_into(dx_b, whT_a, act_a, c_seq_a, dpre_a, dh0a, dc0a, til_a, ws_a, var, done, tn, False, 0, 3)
         free_ctas = max(1, _sms(dev) - Ha // 16 - Hb // 16)
         E.gemm2(dpre_b.view(T * B, 4 * Hb), wxb, out=dx_b.view(T * B, Ha), b_mn=True, ctas=1, bn=256, max_ctas=free_ctas,
-                gate=ws_b[512:], gate_cfg=[2 * (4 * Hb // 64), 32, T + 1, -1, B, 0, 1], done=done, gate_err=ws_b[SYNC_WORDS - 1:], pdl=True)
+                gate=ws_b[_gate_off(var):], gate_cfg=_gate_cfg(var, 2, 4 * Hb // 64, 1, 4 * Hb // 64, T + 1, -1, B, True), done=done,
+                gate_err=ws_b[SYNC_WORDS - 1:], pdl=True)
         STATS["fast_bwd"] += 2
         STATS["kernels"] += 5
         a = ctx.addrs
