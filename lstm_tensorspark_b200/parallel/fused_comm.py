@@ -128,7 +128,10 @@ class FusedComm(TorchDistComm):
         E = ext()
         A = self.arena
         two_shot = (4 * n >= TWO_SHOT_BYTES) if force is None else (force == "two_shot")
-        mc = self._multicast_on() and two_shot
+        # NVLS (in-switch reduction) pays from 3 ranks up; with 2 ranks the peer-pointer kernel is faster stand-alone (measured:
+        # profiles/logs/allreduce_sweep_n2_r2.json) - but it needs 122 registers, so a bucket that has to squeeze onto the SMs a
+        # GEMM leaves idle (pdl) keeps the 32-register multimem variant
+        mc = self._multicast_on() and two_shot and (self.world_size > 2 or pdl or self.use_multicast in ("1", "on", "force"))
         if mode == MODE_AVG and not two_shot:
             off_in_eff = self.off_stage        # one-shot average stages w first
         else:
