@@ -61,6 +61,9 @@ def main():
         variants = [("auto", None, "auto", 0, False), ("one_shot", "one_shot", "0", 0, False), ("two_shot_p2p", "two_shot", "0", 0, False)]
         if comm.arena.mc_base:
             variants.append(("two_shot_nvls", "two_shot", "force", 0, False))
+        if tune and size >= (1 << 22):
+            variants += [("p2p_b128", "two_shot", "0", 128, False), ("p2p_b148", "two_shot", "0", 148, False), ("p2p_b256", "two_shot", "0", 256, False)]
+        if comm.arena.mc_base:
             if tune and size >= (1 << 22):
                 variants += [("nvls_b64", "two_shot", "auto", 64, False), ("nvls_b128", "two_shot", "auto", 128, False),
                              ("nvls_b256", "two_shot", "auto", 256, False)]

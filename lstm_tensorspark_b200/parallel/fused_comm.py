@@ -24,6 +24,7 @@ from .comm import TorchDistComm
 MODE_AVG, MODE_SGD, MODE_ADAM = 0, 1, 2
 TWO_SHOT_BYTES = int(os.environ.get("LSTM_TS_AR_TWO_SHOT_BYTES", str(8 * 1024)))      # measured at 8 GPUs (profiles/logs/sweep8_r2.log): two-shot wins from 16 KB up, ties below
 AR_BLOCKS = int(os.environ.get("LSTM_TS_AR_BLOCKS", "64"))
+AR_BLOCKS_P2P_LARGE = int(os.environ.get("LSTM_TS_AR_BLOCKS_P2P_LARGE", "128"))
 AR_BLOCKS_LARGE = int(os.environ.get("LSTM_TS_AR_BLOCKS_LARGE", "64"))    # messages >= 32 MB (measured: 64 = 128 = 256 blocks, unroll irrelevant: sweep8c.log)
 
 
@@ -149,7 +150,10 @@ class FusedComm(TorchDistComm):
             m, v = m[:n], v[:n]
         if wd_numel >= 0:
             wd_numel = max(0, min(n, wd_numel - elem_off))
-        nblk = blocks or self.blocks_override or (AR_BLOCKS_LARGE if 4 * n >= (32 << 20) else AR_BLOCKS)
+        # grid: the NVLS kernel is switch-bound (64 = 128 = 256 CTAs, profiles/logs); the peer-pointer kernel is bound by bytes in
+        # flight per SM - 128 CTAs from 4 MB up (2 GPUs, 1 GB: 2.00 ms vs 2.57 ms with 64; NCCL 2.20 ms)
+        nblk = blocks or self.blocks_override or ((AR_BLOCKS_P2P_LARGE if 4 * n >= (4 << 20) else AR_BLOCKS) if not mc
+                                                  else (AR_BLOCKS_LARGE if 4 * n >= (32 << 20) else AR_BLOCKS))
         E.fused_allreduce(ptrs, (A.mc(off_in_eff) + e4) if mc else 0, (A.mc(self.off_data) + e4) if mc else 0,
                           (A.mc(self.off_shadow) + e2) if mc else 0, m, v, self.epochs[slot * mb:(slot + 1) * mb], self.err, n, self.rank, self.world_size,
                           mode, two_shot, mc, nblk, lr, b1, b2, eps, wd, float(self.timeout_s), step_dev, wd_numel, bump_step, pdl)
