@@ -109,6 +109,10 @@ struct Gemm2Params {
   unsigned int* done;
   int pdl;                       // launched as a programmatic dependent of the previous kernel (see launch2); waits for it before exiting
   int reverse_m;                 // walk the M tiles from the last to the first (the backward recurrence runs backwards in time)
+  // Folded operand (a batch-major [Bsz, T, F] array read as the time-major matrix [T * Bsz, F] without a transpose pass): the
+  // tensor map describes the storage as [fold = Bsz rows][T * F columns]; logical row r lives at storage row r % fold, columns
+  // (r / fold) * fold_cols + [0, F).  a_fold: the K-major A operand (rows = M);  b_fold: the MN-major B operand (rows = K).
+  int a_fold, b_fold, fold_cols;
 };
 
 template <int kCtas, int BN, bool kAMN, bool kBMN, int kOut>
@@ -194,22 +198,28 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           gate_t_ok = t;
         }
       }
+      // folded K-major A: the tile's 128 rows are 128 consecutive storage rows of ONE time step (fold % 128 == 0)
+      const int a_col = (!kAMN && p.a_fold) ? (m0 / p.a_fold) * p.fold_cols : 0;
+      const int a_row = (!kAMN && p.a_fold) ? m0 % p.a_fold : m0;
       for (int kb = 0, k0 = 0; kb < num_kb; ++kb, k0 += BK) {
         const uint32_t eb = empty0 + 8 * stage, fb = full0 + 8 * stage, fbl = full0_leader + 8 * stage;
         while (!tc::mbar_try_wait_u32(eb, phase ^ 1)) {}
         if (tc::elect_one()) {
           if (leader) tc::mbar_expect_tx_u32(fb, C::kStageBytes * kCtas);
           const uint32_t sa = sa0 + stage * C::kABytes, sb = sb0 + stage * C::kBBytes;
+          // folded MN-major B: the k-block's 64 rows are 64 consecutive storage rows of one time step (fold % 64 == 0)
+          const int b_col = (kBMN && p.b_fold) ? (k0 / p.b_fold) * p.fold_cols : 0;
+          const int b_row = (kBMN && p.b_fold) ? k0 % p.b_fold : k0;
           if (kCtas == 2) {
             if (kAMN) {
 #pragma unroll
               for (int j = 0; j < BM / 64; ++j) tma_load_2d_pair(sa + j * 8192, &tmap_a, fbl, m0 + 64 * j, k0);
             } else {
-              tma_load_2d_pair(sa, &tmap_a, fbl, k0, m0);
+              tma_load_2d_pair(sa, &tmap_a, fbl, k0 + a_col, a_row);
             }
             if (kBMN) {
 #pragma unroll
-              for (int j = 0; j < C::kBNCta / 64; ++j) tma_load_2d_pair(sb + j * 8192, &tmap_b, fbl, n0 + 64 * j, k0);
+              for (int j = 0; j < C::kBNCta / 64; ++j) tma_load_2d_pair(sb + j * 8192, &tmap_b, fbl, n0 + 64 * j + b_col, b_row);
             } else {
               tma_load_2d_pair(sb, &tmap_b, fbl, k0, n0);
             }
@@ -218,11 +228,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 #pragma unroll
               for (int j = 0; j < BM / 64; ++j) tc::tma_load_2d_u32(sa + j * 8192, &tmap_a, fb, m0 + 64 * j, k0);
             } else {
-              tc::tma_load_2d_u32(sa, &tmap_a, fb, k0, m0);
+              tc::tma_load_2d_u32(sa, &tmap_a, fb, k0 + a_col, a_row);
             }
             if (kBMN) {
 #pragma unroll
-              for (int j = 0; j < C::kBNCta / 64; ++j) tc::tma_load_2d_u32(sb + j * 8192, &tmap_b, fb, n0 + 64 * j, k0);
+              for (int j = 0; j < C::kBNCta / 64; ++j) tc::tma_load_2d_u32(sb + j * 8192, &tmap_b, fb, n0 + 64 * j + b_col, b_row);
             } else {
               tc::tma_load_2d_u32(sb, &tmap_b, fb, k0, n0);
             }
@@ -367,8 +377,10 @@ int launch2(const void* A, const void* B, const Gemm2Params& p, int lda, int ldb
   CUtensorMap ta, tb;
   // K-major operand: [rows = M|N][cols = K];  MN-major operand: [rows = K][cols = M|N]
   if (kAMN) { if (int rc = ts::make_tmap_2d_bf16(&ta, A, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)lda, 64, BK)) return rc; }
+  else if (p.a_fold) { if (int rc = ts::make_tmap_2d_bf16(&ta, A, (uint64_t)p.a_fold, (uint64_t)(p.M / p.a_fold) * p.fold_cols, (uint64_t)lda, BK, BM)) return rc; }
   else      { if (int rc = ts::make_tmap_2d_bf16(&ta, A, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)lda, BK, BM)) return rc; }
-  if (kBMN) { if (int rc = ts::make_tmap_2d_bf16(&tb, B, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)ldb, 64, BK)) return rc; }
+  if (kBMN && p.b_fold) { if (int rc = ts::make_tmap_2d_bf16(&tb, B, (uint64_t)p.b_fold, (uint64_t)(p.K / p.b_fold) * p.fold_cols, (uint64_t)ldb, 64, BK)) return rc; }
+  else if (kBMN) { if (int rc = ts::make_tmap_2d_bf16(&tb, B, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)ldb, 64, BK)) return rc; }
   else      { if (int rc = ts::make_tmap_2d_bf16(&tb, B, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)ldb, BK, C::kBNCta)) return rc; }
   auto kern = gemm2_kernel<kCtas, BN, kAMN, kBMN, kOut>;
   static bool attr_set = false;
@@ -427,11 +439,20 @@ int launch_major(const void* A, const void* B, const Gemm2Params& p, int lda, in
 // gate_cfg[7] = {count, stride (u32 words), base, per_step, rows_per_step, use_last, reverse_m} (see Gemm2Params); max_ctas > 0 caps the grid.
 extern "C" int ts_gemm2(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, int lda, int ldb, int ldc,
                         int a_mn, int b_mn, int out_mode, int ctas, int bn, int dev, int max_ctas, const unsigned int* gate,
-                        const int* gate_cfg, unsigned int* done, int* gate_err, int pdl, cudaStream_t st) {
+                        const int* gate_cfg, unsigned int* done, int* gate_err, int pdl, int a_fold, int b_fold, int fold_cols,
+                        cudaStream_t st) {
   if (K % 8 != 0 || lda % 8 != 0 || ldb % 8 != 0) { ts::set_last_error("gemm2: K and the operand pitches must be multiples of 8"); return -2; }
   if ((a_mn && M % 8 != 0) || (b_mn && N % 8 != 0) || N % 8 != 0) { ts::set_last_error("gemm2: M (MN-major A) / N must be multiples of 8"); return -2; }
+  // folded operands (see Gemm2Params): no tile / k-block may straddle two time steps or run past a time step's columns
+  if (a_fold && (a_mn || gate != nullptr || a_fold % 128 != 0 || M % a_fold != 0 || K % 64 != 0 || fold_cols < K)) {
+    ts::set_last_error("gemm2: folded A needs a K-major ungated operand, fold % 128 == 0, M % fold == 0, K % 64 == 0"); return -2;
+  }
+  if (b_fold && (!b_mn || b_fold % 64 != 0 || K % b_fold != 0 || N % bn != 0 || fold_cols < N)) {
+    ts::set_last_error("gemm2: folded B needs an MN-major operand, fold % 64 == 0, K % fold == 0, N % bn == 0"); return -2;
+  }
   Gemm2Params p{};
   p.C = C; p.bias = bias; p.M = M; p.N = N; p.K = K; p.ldc = ldc;
+  p.a_fold = a_fold; p.b_fold = b_fold; p.fold_cols = fold_cols;
   p.gate = gate; p.gate_err = gate_err; p.done = done; p.pdl = pdl;
   if (gate != nullptr) {
     p.gate_count = gate_cfg[0]; p.gate_stride = gate_cfg[1]; p.gate_base = gate_cfg[2]; p.gate_per_step = gate_cfg[3];

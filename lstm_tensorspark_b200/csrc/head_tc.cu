@@ -65,6 +65,14 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const HeadParams 
     tc::fence_barrier_init();
   }
   if (warp == 1) { tc::tmem_alloc(tmem_slot, tmem_cols); tc::tmem_relinquish(); }
+  // the first pass over the ring needs no empty-barrier wait: start streaming h while the weight image is being built
+  const int pre_kb = num_kb < kHStages ? num_kb : kHStages;
+  if (threadIdx.x == 0) {
+    for (int kb = 0; kb < pre_kb; ++kb) {
+      tc::mbar_expect_tx(&full[kb], HM * HK * 2);
+      tc::tma_load_2d(smem_a + kb * (HM * HK * 2), &tmap_h, &full[kb], kb * HK, m0);
+    }
+  }
   for (int c = threadIdx.x; c < p.NP; c += kHThreads) bias_s[c] = c < p.C ? p.bias[c] : 0.f;
   // weight image: element (n = class, k) -> block k/64, row n, 16 B chunk ((k%64)/8) ^ (n&7), 2 B slot k%8.  First zero the
   // image (padding rows C..NP and a ragged last k-block), then walk W [H, C] linearly: coalesced fp32 reads, one bf16 store each.
@@ -73,12 +81,21 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const HeadParams 
     for (int i = threadIdx.x; i < img16; i += kHThreads) reinterpret_cast<uint4*>(smem_w)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     const int total = p.H * p.C;
-    for (int i = threadIdx.x; i < total; i += kHThreads) {
-      const int k = i / p.C, n = i - k * p.C;
-      const float w = p.W[i];
-      const int kb = k / HK, kk = k % HK;
-      const uint32_t off = (uint32_t)kb * wblk + (uint32_t)n * 128 + (uint32_t)((((kk >> 3) ^ (n & 7)) << 4) + ((kk & 7) << 1));
-      *reinterpret_cast<__nv_bfloat16*>(smem_w + off) = __float2bfloat16_rn(w);
+    constexpr int kWU = 8;                                         // loads in flight per thread: the walk is pure L2 latency otherwise
+    for (int i0 = threadIdx.x; i0 < total; i0 += kHThreads * kWU) {
+      float w[kWU];
+#pragma unroll
+      for (int u = 0; u < kWU; ++u) { const int i = i0 + u * kHThreads; w[u] = i < total ? __ldg(p.W + i) : 0.f; }
+#pragma unroll
+      for (int u = 0; u < kWU; ++u) {
+        const int i = i0 + u * kHThreads;
+        if (i < total) {
+          const int k = i / p.C, n = i - k * p.C;
+          const int kb = k / HK, kk = k % HK;
+          const uint32_t off = (uint32_t)kb * wblk + (uint32_t)n * 128 + (uint32_t)((((kk >> 3) ^ (n & 7)) << 4) + ((kk & 7) << 1));
+          *reinterpret_cast<__nv_bfloat16*>(smem_w + off) = __float2bfloat16_rn(w[u]);
+        }
+      }
     }
   }
   tc::fence_proxy_async();                       // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -88,8 +105,8 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const HeadParams 
   const uint32_t tmem_d = *tmem_slot;
 
   if (warp == 0) {
-    uint32_t stage = 0, phase = 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
+    uint32_t stage = pre_kb == kHStages ? 0 : pre_kb, phase = pre_kb == kHStages ? 1 : 0;
+    for (int kb = pre_kb; kb < num_kb; ++kb) {
       while (!tc::mbar_try_wait(&empty[stage], phase ^ 1)) {}
       if (tc::elect_one()) {
         tc::mbar_expect_tx(&full[stage], HM * HK * 2);
@@ -193,22 +210,41 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const T* __restrict__ h, 
   const int b0 = blockIdx.y * rows_per_block;
   const int nb = min(rows_per_block, B - b0);
   const float scale = dloss ? *dloss : 1.f;
-  for (int i = threadIdx.x; i < nb * CP; i += 128) {
-    const int b = i / CP, c = i % CP;
-    ds[i] = c < C ? dlogits[(size_t)(b0 + b) * C + c] * scale : 0.f;
+  {
+    constexpr int kLU = 8;                              // slab loads in flight per thread
+    for (int i0 = threadIdx.x; i0 < nb * CP; i0 += 128 * kLU) {
+      float v[kLU];
+#pragma unroll
+      for (int u = 0; u < kLU; ++u) {
+        const int i = i0 + u * 128, b = i / CP, c = i % CP;
+        v[u] = (i < nb * CP && c < C) ? __ldg(dlogits + (size_t)(b0 + b) * C + c) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kLU; ++u) { const int i = i0 + u * 128; if (i < nb * CP) ds[i] = v[u] * scale; }
+    }
   }
   __syncthreads();
   float w[CP], acc[CP];
 #pragma unroll
   for (int c = 0; c < CP; ++c) { w[c] = (j < H && c < C) ? W[(size_t)j * C + c] : 0.f; acc[c] = 0.f; }
   if (j < H) {
-    for (int b = q; b < nb; b += 4) {
-      const float hv = ts::Cvt<T>::to_f(h[(size_t)(b0 + b) * H + j]);
-      const float* d = ds + b * CP;
-      float s = 0.f;
+    constexpr int kU = 8;                                // h loads in flight per thread (the loop is L2-latency bound otherwise)
+    for (int bb = q; bb < nb; bb += 4 * kU) {
+      T hraw[kU];
 #pragma unroll
-      for (int c = 0; c < CP; ++c) { s = fmaf(d[c], w[c], s); acc[c] = fmaf(hv, d[c], acc[c]); }
-      dh[(size_t)(b0 + b) * H + j] = ts::Cvt<TDH>::from_f(s);
+      for (int u = 0; u < kU; ++u) { const int b = bb + 4 * u; hraw[u] = h[(size_t)(b0 + (b < nb ? b : bb)) * H + j]; }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int b = bb + 4 * u;
+        if (b < nb) {
+          const float hv = ts::Cvt<T>::to_f(hraw[u]);
+          const float* d = ds + b * CP;
+          float s = 0.f;
+#pragma unroll
+          for (int c = 0; c < CP; ++c) { s = fmaf(d[c], w[c], s); acc[c] = fmaf(hv, d[c], acc[c]); }
+          dh[(size_t)(b0 + b) * H + j] = ts::Cvt<TDH>::from_f(s);
+        }
+      }
     }
   }
 #pragma unroll

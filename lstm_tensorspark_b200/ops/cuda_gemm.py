@@ -43,11 +43,37 @@ def _tc_ok(a_k: torch.Tensor, b_k: torch.Tensor, M: int, N: int, K: int) -> bool
     return True
 
 
-def matmul(a: torch.Tensor, b_t: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False,
-           out_dtype: Optional[torch.dtype] = None, bias: Optional[torch.Tensor] = None, max_ctas: int = 0) -> torch.Tensor:
+def folded_ok(x_bm: torch.Tensor) -> bool:
+    """Can a batch-major ``[B, T, F]`` array be read in place as the time-major matrix ``[T*B, F]`` by the tensor-core GEMM
+    (see ``Gemm2Params::a_fold`` in csrc/gemm2_tcgen05.cu)?  Saves the transpose pass over the input of the first layer."""
+    return (x_bm.is_cuda and x_bm.dim() == 3 and x_bm.dtype == torch.bfloat16 and x_bm.is_contiguous() and x_bm.shape[0] % 128 == 0
+            and x_bm.shape[2] % max(64, GEMM_BN) == 0 and x_bm.data_ptr() % 16 == 0 and GEMM_BN in (128, 256))
+
+
+def matmul(a: Optional[torch.Tensor], b_t: Optional[torch.Tensor], out: Optional[torch.Tensor] = None, accumulate: bool = False,
+           out_dtype: Optional[torch.dtype] = None, bias: Optional[torch.Tensor] = None, max_ctas: int = 0,
+           a_folded: Optional[torch.Tensor] = None, b_folded: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``a [M,K] @ b_t[N,K]^T`` (+ bias[N]); either operand may be a transposed view (then it is MN-major and is read in
-    place).  ``out`` fp32 + ``accumulate`` -> ``out += a @ b_t^T``."""
+    place).  ``out`` fp32 + ``accumulate`` -> ``out += a @ b_t^T``.
+
+    ``a_folded`` / ``b_folded`` (instead of ``a`` / ``b_t``): a batch-major ``[B, T, F]`` array (``folded_ok``) standing for the
+    time-major matrix ``X = [T*B, F]``: ``a = X`` resp. ``b_t = X^T``."""
     E = ext()
+    if a_folded is not None or b_folded is not None:
+        xb = a_folded if a_folded is not None else b_folded
+        Bsz, T, F = xb.shape
+        store = xb.view(Bsz, T * F)
+        other = _major(b_t if a_folded is not None else a)
+        assert folded_ok(xb) and other is not None and other[1].dtype == torch.bfloat16 and (a_folded is None or b_folded is None)
+        if out_dtype is None:
+            out_dtype = out.dtype if out is not None else torch.bfloat16
+        STATS["tc"] += 1
+        if a_folded is not None:
+            return E.gemm2(store, other[1], bias=bias, out=out, a_mn=False, b_mn=other[0], out_fp32=out_dtype == torch.float32,
+                           accumulate=accumulate, ctas=GEMM_CTAS, bn=GEMM_BN if b_t.shape[0] > 128 else 128, max_ctas=max_ctas,
+                           a_fold=Bsz, fold_cols=F)
+        return E.gemm2(other[1], store, bias=bias, out=out, a_mn=other[0], b_mn=True, out_fp32=out_dtype == torch.float32,
+                       accumulate=accumulate, ctas=GEMM_CTAS, bn=GEMM_BN, max_ctas=max_ctas, b_fold=Bsz, fold_cols=F)
     M, K = a.shape
     N = b_t.shape[0]
     assert b_t.shape[1] == K, (a.shape, b_t.shape)
@@ -60,6 +86,7 @@ def matmul(a: torch.Tensor, b_t: torch.Tensor, out: Optional[torch.Tensor] = Non
         STATS["tc"] += 1
         return E.gemm2(ma[1], mb[1], bias=bias, out=out, a_mn=ma[0], b_mn=mb[0], out_fp32=out_dtype == torch.float32,
                        accumulate=accumulate, ctas=GEMM_CTAS, bn=GEMM_BN if N > 128 else 128, max_ctas=max_ctas)
+    assert a_folded is None and b_folded is None, "folded operands need the tensor-core path (check folded_ok first)"
     STATS["generic"] += 1
     a_g = a if a.dtype in (torch.float32, torch.bfloat16) else a.float()
     b_g = b_t if b_t.dtype in (torch.float32, torch.bfloat16) else b_t.float()

@@ -104,18 +104,20 @@ def grad_sink(w_addr: int):
     return ent[1], owner.take_sink(w_addr)
 
 
-def _accumulate_grad(w_addr: int, a_t: torch.Tensor, b: torch.Tensor):
+def _accumulate_grad(w_addr: int, a_t: torch.Tensor, b: torch.Tensor, b_folded: bool = False):
     """dW = a_t @ b in fp32 (``a_t`` = dG^T as a transposed view, ``b`` = the layer input: both operands MN-major, read in
-    place by the tcgen05 GEMM).  When the parameter lives in a FlatParams buffer the product lands straight in its grad
+    place by the tcgen05 GEMM; ``b_folded``: ``b`` is the batch-major [B,T,D] array standing for the time-major [T*B, D]
+    matrix).  When the parameter lives in a FlatParams buffer the product lands straight in its grad
     view (overwrite on the first write of a step, accumulate afterwards) and None is returned to autograd."""
+    ops = dict(a=a_t, b_t=None, b_folded=b) if b_folded else dict(a=a_t, b_t=b.t())
     sink = grad_sink(w_addr)
     if sink is not None:
         _big_launch_begin()
-        G.matmul(a_t, b.t(), out=sink[0], accumulate=sink[1])
+        G.matmul(out=sink[0], accumulate=sink[1], **ops)
         _after_big_launch()                  # finished buckets of earlier gradients: allreduce them under this GEMM
         _grads_written()
         return None
-    return G.matmul(a_t, b.t(), out_dtype=torch.float32)
+    return G.matmul(out_dtype=torch.float32, **ops)
 
 
 _BIAS_SPLIT = {}
@@ -377,6 +379,7 @@ def lstm_layer_sequence(x_seq, h0, c0, w_x, w_h, bias):
 # The reference stacks layers strictly one after the other (/root/reference/src/models/recurrent/rnn.py:38-42); here layer l+1
 # trails layer l by a couple of time steps and the next layer's input projection leaves the critical path altogether.
 # =====================================================================================================================
+FOLDED_FEED = os.environ.get("LSTM_TS_FOLDED_FEED", "1") != "0"   # batch-major input read in place by the first layer's GEMMs
 WAVEFRONT = os.environ.get("LSTM_TS_WAVEFRONT", "1") == "1"
 _SIDE_STREAMS = {}
 _WS_PAIR = {}
@@ -462,13 +465,20 @@ class _LSTMPairFn(torch.autograd.Function):
         T, B, D = x_seq.shape
         Ha, Hb = w_ha.shape[1], w_hb.shape[1]
         cd = x_seq.dtype
-        x2d = x_seq.reshape(T * B, D).contiguous()
+        # a batch-major input ([B,T,D] storage behind a transposed view) is read in place by the x-projection and by the
+        # weight-gradient GEMM of the first layer (folded tensor map, csrc/gemm2_tcgen05.cu): no transpose pass
+        x_bm = x_seq.transpose(0, 1) if not x_seq.is_contiguous() else None
+        x2d = x_seq.reshape(T * B, D) if x_bm is None else x_bm
         wxa, wha, wxb, whb = _lowp(w_xa, cd), _lowp(w_ha, cd), _lowp(w_xb, cd), _lowp(w_hb, cd)
         ba_f, bb_f = b_a.detach().float().contiguous(), b_b.detach().float().contiguous()
         h0a_c, h0b_c = h0a.detach().to(cd).contiguous(), h0b.detach().to(cd).contiguous()
         c0a_f, c0b_f = c0a.detach().float().contiguous(), c0b.detach().float().contiguous()
         _warm_wavefront_kernels(dev)
-        gx_a = _gemm_tn(x2d, wxa).view(T, B, 4 * Ha)
+        if x_bm is None:
+            gx_a = _gemm_tn(x2d, wxa).view(T, B, 4 * Ha)
+        else:
+            STATS["tc_gemm"] += 1; STATS["kernels"] += 1; STATS["folded_feed"] = STATS.get("folded_feed", 0) + 1
+            gx_a = G.matmul(None, wxa, out_dtype=cd, a_folded=x_bm).view(T, B, 4 * Ha)
         opt = dict(dtype=cd, device=dev)
         h_seq_a = torch.empty(T + 1, B, Ha, **opt); c_seq_a = torch.empty(T + 1, B, Ha, dtype=torch.float32, device=dev)
         act_a = torch.empty(T, B, 4 * Ha, **opt); til_a = torch.empty((T + 1) * 2 * 128 * Ha, **opt)
@@ -498,6 +508,7 @@ class _LSTMPairFn(torch.autograd.Function):
         ctx.save_for_backward(x2d, h_seq_a, c_seq_a, act_a, h_seq_b, c_seq_b, act_b, wxa, wha, wxb, whb)
         ctx.set_materialize_grads(False)
         ctx.dims = (T, B, D, Ha, Hb)
+        ctx.x_folded = x_bm is not None
         ctx.addrs = (w_xa.data_ptr(), w_ha.data_ptr(), b_a.data_ptr(), w_xb.data_ptr(), w_hb.data_ptr(), b_b.data_ptr())
         ctx.in_dtypes = (h0a.dtype, c0a.dtype, h0b.dtype, c0b.dtype)
         return h_seq_b[1:], h_seq_a[T], c_seq_a[T], h_seq_b[T], c_seq_b[T]
@@ -540,12 +551,12 @@ class _LSTMPairFn(torch.autograd.Function):
         dw_hb = _accumulate_grad(a[4], dg_b.t(), h_seq_b[:T].reshape(T * B, Hb))
         db_b = _bias_grad(a[5], dg_b, under_gemm=dw_hb is None, part=1)
         dg_a = dpre_a.view(T * B, 4 * Ha)
-        dw_xa = _accumulate_grad(a[0], dg_a.t(), x2d)
+        dw_xa = _accumulate_grad(a[0], dg_a.t(), x2d, b_folded=ctx.x_folded)
         _bias_grad(a[2], dg_a, under_gemm=dw_xa is None, part=0)
         dw_ha = _accumulate_grad(a[1], dg_a.t(), h_seq_a[:T].reshape(T * B, Ha))
         db_a = _bias_grad(a[2], dg_a, under_gemm=dw_ha is None, part=1)
         dx = None
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0]:                                       # (never with a folded input: lstm_pair_sequence)
             dx = G.matmul(dg_a, wxa.t(), out_dtype=cd).view(T, B, D)
             STATS["kernels"] += 1
         t = ctx.in_dtypes
@@ -556,6 +567,8 @@ def lstm_pair_sequence(x_seq, la, lb):
     """Two stacked layers as one wavefront op.  ``la`` / ``lb`` = (h0, c0, w_x, w_h, bias).  -> (h_seq_b, hT_a, cT_a, hT_b, cT_b)."""
     if (not x_seq.is_contiguous() and not x_seq.requires_grad and x_seq.transpose(0, 1).is_contiguous()
             and (x_seq.shape[2] * x_seq.element_size()) % 16 == 0):
+        if FOLDED_FEED and G.folded_ok(x_seq.transpose(0, 1)):
+            return _LSTMPairFn.apply(x_seq, *la, *lb)                     # read in place (see forward)
         x_seq = ext().transpose01(x_seq.transpose(0, 1))
         STATS["kernels"] += 1
     return _LSTMPairFn.apply(x_seq.contiguous(), *la, *lb)

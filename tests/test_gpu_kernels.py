@@ -129,6 +129,32 @@ def test_tcgen05_gemm2(E, dev, ctas, bn, a_mn, b_mn):
         assert (acc - R).abs().max() / scale < 2e-3
 
 
+@pytest.mark.parametrize("ctas,bn", [(1, 128), (2, 256)])
+@pytest.mark.parametrize("Bsz,T,F", [(128, 3, 128), (256, 5, 256), (384, 2, 512)])
+def test_tcgen05_gemm2_folded_batch_major_operand(E, dev, ctas, bn, Bsz, T, F):
+    """A batch-major [B,T,F] array read in place as the time-major matrix X = [T*B, F] (folded tensor map): X @ W^T (the
+    x-projection) and dG^T @ X (the weight gradient of the first layer) against the same products over a transposed copy."""
+    torch.manual_seed(1)
+    x_bm = (torch.randn(Bsz, T, F, device=dev) * 0.5).bfloat16()
+    X = x_bm.transpose(0, 1).reshape(T * Bsz, F)                      # time-major copy
+    store = x_bm.view(Bsz, T * F)
+    W = (torch.randn(520, F, device=dev) * 0.5).bfloat16()
+    R = X.float() @ W.float().t()
+    C = E.gemm2(store, W, out_fp32=True, ctas=ctas, bn=bn, a_fold=Bsz, fold_cols=F)
+    assert C.shape == R.shape and (C - R).abs().max() / float(R.abs().max()) < 2e-3
+    if F % bn:
+        return                                                        # a folded B operand needs N % bn == 0
+    dG = (torch.randn(T * Bsz, 384, device=dev) * 0.5).bfloat16()     # dW = dG^T @ X: A = dG^T (MN-major), B = X (MN-major, folded)
+    R2 = dG.float().t() @ X.float()
+    acc = torch.full((384, F), 2.0, device=dev)
+    E.gemm2(dG, store, out=acc, a_mn=True, b_mn=True, accumulate=True, ctas=ctas, bn=bn, b_fold=Bsz, fold_cols=F)
+    assert (acc - 2.0 - R2).abs().max() / float(R2.abs().max()) < 2e-3
+    from lstm_tensorspark_b200.ops import cuda_gemm as G
+    if G.folded_ok(x_bm):
+        assert torch.equal(G.matmul(None, W, a_folded=x_bm), G.matmul(X, W))
+        assert torch.equal(G.matmul(dG.t(), None, b_folded=x_bm, out_dtype=torch.float32), G.matmul(dG.t(), X.t(), out_dtype=torch.float32))
+
+
 @pytest.mark.parametrize("M,N,K,dt", [(10, 64, 4, torch.float32), (33, 20, 48, torch.bfloat16), (150, 3, 16, torch.float32), (64, 4, 650, torch.bfloat16)])
 def test_generic_gemm_and_dispatch(E, dev, M, N, K, dt):
     """CUDA-core GEMM for the shapes the tensor-core kernels cannot take (the reference's iris configuration)."""
