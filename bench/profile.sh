@@ -31,7 +31,7 @@ case "$what" in
     LSTM_TS_WAVEFRONT=1 python bench/trace_step.py > gpurun_out/trace_step.out 2>&1 ;;
   sanitize)
     for tool in memcheck racecheck synccheck; do
-      compute-sanitizer --tool $tool python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "pointwise or head_forward or adam or (gemm2 and 1-128) or (persistent and 3-128-64-64) or generic" > gpurun_out/sanitizer_$tool.log 2>&1
+      compute-sanitizer --tool $tool python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "pointwise or head_forward or adam or (gemm2 and 1-128) or (persistent and 3-128-64-64) or generic or (folded and 128-3-128)" > gpurun_out/sanitizer_$tool.log 2>&1
       tail -3 gpurun_out/sanitizer_$tool.log
     done ;;
 esac
