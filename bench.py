@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--seq_len", type=int, default=MODEL["seq_len"])
     ap.add_argument("--batch_size", type=int, default=MODEL["batch_size"])
     ap.add_argument("--no_e2e", action="store_true")
+    ap.add_argument("--e2e_depth", type=int, default=2, help="staging slots of the end-to-end loader (copy enqueued depth-1 steps ahead)")
+    ap.add_argument("--bind_inputs", type=int, default=1, help="1 = CUDA graphs captured on the input buffers themselves (no staging copy)")
     ap.add_argument("--config", type=int, default=3, choices=[3, 4],
                     help="BASELINE.json config: 3 = 2x1024 T=128 B=256 per-step grad allreduce (headline); "
                          "4 = 4x2048 T=512 B=64 per-epoch parameter average (one average inside the timed region)")
@@ -216,6 +218,7 @@ def run_baseline_arm(torch, dist, args, hidden, D, C, B, T, rank, world, device,
     sys.path.insert(0, os.path.join(ROOT, "baseline"))
     import harness
     runner = harness.BaselineRunner(hidden, D, C, B, T, rank, world, device, optimizer=args.optimizer, variant=variant)
+    runner.bind_inputs = bool(args.bind_inputs) and args.config == 3      # same input binding as our arm
     step_dev, step_e2e, h2d, d2h, launches, cfg_extra = runner.make_steps()
     ms, clk, e2e = measure(torch, dist, world, device, local, step_dev, step_e2e, args.steps, args.warmup, args.no_e2e, B, world, h2d, d2h)
     res = {"value": B * world * args.steps / (ms / 1e3), "ms_per_step": ms / args.steps, "clocks": clk, "e2e": e2e, "config": cfg_extra}
@@ -325,9 +328,13 @@ def main():
             eng.maybe_average()                       # config 4: the per-epoch parameter average (every `steps` steps)
             return loss
 
-        loader = Dm.PinnedHostLoader(xs, ys, B, device, dtype=torch.bfloat16, shuffle=False, seed=rank)
-        loss_host = torch.empty(2, dtype=torch.float32, pin_memory=True)
-        loss_evt = [torch.cuda.Event(), torch.cuda.Event()]
+        loader = Dm.PinnedHostLoader(xs, ys, B, device, dtype=torch.bfloat16, shuffle=False, seed=rank, depth=args.e2e_depth)
+        e2e_dbg = os.environ.get("LSTM_TS_E2E_DEBUG", "")              # diagnostics: "nocopy" (no H2D DMA), "lagN" (read the loss N steps late)
+        loader.debug_skip_copy = "nocopy" in e2e_dbg
+        lag = int(e2e_dbg.split("lag")[1][0]) if "lag" in e2e_dbg else 1
+        nslot = lag + 1
+        loss_host = torch.empty(nslot, dtype=torch.float32, pin_memory=True)
+        loss_evt = [torch.cuda.Event() for _ in range(nslot)]
         e2e_state = {"i": 0, "last": float("nan")}
 
         def step_e2e():
@@ -338,11 +345,11 @@ def main():
             x, y = loader.next()
             loss = eng.step(x, y)
             eng.maybe_average()
-            loss_host[i & 1].copy_(loss.float(), non_blocking=True)
-            loss_evt[i & 1].record()
-            if i > 0:
-                loss_evt[(i - 1) & 1].synchronize()
-                e2e_state["last"] = float(loss_host[(i - 1) & 1])     # the previous step's loss, on the host
+            loss_host[i % nslot].copy_(loss.float(), non_blocking=True)
+            loss_evt[i % nslot].record()
+            if i >= lag:
+                loss_evt[(i - lag) % nslot].synchronize()
+                e2e_state["last"] = float(loss_host[(i - lag) % nslot])     # the previous step's loss, on the host
             e2e_state["i"] = i + 1
             return loss_host
 
@@ -356,11 +363,24 @@ def main():
         want_graph = args.cuda_graph != 0           # default: capture the whole step (fwd + bwd + fused allreduce/update) once, replay it
         if want_graph:
             try:
-                eng.capture(dev_x[:B], dev_y[:B])
+                # graphs captured directly on the buffers the batches arrive in (the 4 device batches of the device-timed loop,
+                # the loader's 2 staging slots of the end-to-end loop): no 67 MB staging copy per step.  Config 4: 10 GB of
+                # activations per graph and a 50 ms step - not worth seven graphs.
+                bind = ([(dev_x[i * B:(i + 1) * B], dev_y[i * B:(i + 1) * B]) for i in range(nb)] + list(loader.dev)) \
+                    if (args.bind_inputs and args.config == 3) else []
+                try:
+                    eng.capture(dev_x[:B], dev_y[:B], bind=bind)
+                except Exception as e:                  # noqa: BLE001  (e.g. out of memory for seven graphs): one staged graph
+                    if not bind:
+                        raise
+                    graph_err = "bound capture failed, staged graph instead: " + repr(e)[:160]
+                    eng._graph, eng._bound = None, {}
+                    torch.cuda.synchronize(device)
+                    eng.capture(dev_x[:B], dev_y[:B])
                 graphed = True
             except Exception as e:                      # noqa: BLE001
                 graph_err = repr(e)[:200]
-                eng._graph = None
+                eng._graph, eng._bound = None, {}
                 torch.cuda.synchronize(device)
         h2d, d2h = loader.bytes_per_batch, 4
         ms, clk, e2e = measure(torch, dist, world, device, local, step_dev, step_e2e, args.steps, args.warmup, args.no_e2e, B, n_gpus, h2d, d2h)
@@ -368,6 +388,8 @@ def main():
         if hasattr(comm, "check_errors"):
             comm.check_errors()
         cfg_extra = {"comm": comm.name, "fast_path": cuda_lstm.STATS["fast_fwd"] > 0, "cuda_graph": graphed, "optimizer": args.optimizer,
+                     "graph_inputs": "bound (one graph per input buffer, no staging copy)" if (graphed and eng._bound) else "staged",
+                     "e2e_loader_depth": args.e2e_depth,
                      "grad_buckets": bool(eng._bucket_plan)}
         if graph_err:
             cfg_extra["cuda_graph_error"] = graph_err

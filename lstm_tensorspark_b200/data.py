@@ -191,12 +191,18 @@ class DeviceShard:
             self._perm = torch.arange(self.n, device=self.x.device)
         self._i = 0
 
-    def next(self) -> Tuple[torch.Tensor, torch.Tensor]:
+    def next(self, out=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``out = (x_buf, y_buf)``: gather the batch straight into these buffers (the input buffers of a captured CUDA graph:
+        ``TrainEngine.graph_inputs()``) instead of into fresh tensors that then have to be copied there."""
         if self._perm is None or self._i >= self.per_epoch:
             self._reshuffle()
         lo = self._i * self.batch_size
         idx = self._perm[lo:lo + self.batch_size]
         self._i += 1
+        if out is not None and out[0].shape[0] == idx.numel() and out[0].dtype == self.x.dtype:
+            torch.index_select(self.x, 0, idx, out=out[0])
+            torch.index_select(self.y, 0, idx, out=out[1])
+            return out[0], out[1]
         return self.x.index_select(0, idx), self.y.index_select(0, idx)
 
     def state_dict(self):
@@ -215,9 +221,12 @@ class PinnedHostLoader:
     Shuffling permutes the pinned copy once per pass (not per step), so a step is exactly one H2D DMA per tensor."""
 
     def __init__(self, x: np.ndarray, y: np.ndarray, batch_size: int, device, dtype=torch.float32,
-                 shuffle: bool = True, seed: int = 0):
+                 shuffle: bool = True, seed: int = 0, depth: int = 2):
+        """``depth``: device staging slots (the copy of a batch is enqueued ``depth - 1`` calls before it is handed out)."""
+        assert depth >= 2
         self.device = torch.device(device)
         self.dtype = dtype
+        self.depth = depth
         self.n = x.shape[0]
         self.batch_size = resolve_batch_size(batch_size, self.n)
         self.per_epoch = self.n // self.batch_size
@@ -232,10 +241,11 @@ class PinnedHostLoader:
             self.y_host = self.y_host.pin_memory()
         shape_x = (self.batch_size,) + tuple(self.x_host.shape[1:])
         self.dev = [(torch.empty(shape_x, dtype=dtype, device=self.device),
-                     torch.empty((self.batch_size,), dtype=torch.int64, device=self.device)) for _ in range(2)]
+                     torch.empty((self.batch_size,), dtype=torch.int64, device=self.device)) for _ in range(depth)]
         self._slot = 0
-        self._pending = None
+        self._pending = []
         self._copy_stream = None
+        self.debug_skip_copy = False
         self._i = self.per_epoch if shuffle else 0
         self.bytes_per_batch = self.dev[0][0].numel() * self.dev[0][0].element_size() + self.batch_size * 8
 
@@ -262,7 +272,7 @@ class PinnedHostLoader:
         """Enqueue the H2D copy of the next batch on the copy stream into the free staging slot."""
         lo = self._advance()
         dx, dy = self.dev[self._slot]
-        self._slot ^= 1
+        self._slot = (self._slot + 1) % self.depth
         if self.device.type != "cuda":
             dx.copy_(self.x_host[lo:lo + self.batch_size])
             dy.copy_(self.y_host[lo:lo + self.batch_size])
@@ -272,8 +282,9 @@ class PinnedHostLoader:
         # the slot being overwritten was consumed by compute work already enqueued on the current stream
         self._copy_stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self._copy_stream):
-            dx.copy_(self.x_host[lo:lo + self.batch_size], non_blocking=True)
-            dy.copy_(self.y_host[lo:lo + self.batch_size], non_blocking=True)
+            if not self.debug_skip_copy:                  # (bench diagnostics only: how much of a step is the DMA's interference?)
+                dx.copy_(self.x_host[lo:lo + self.batch_size], non_blocking=True)
+                dy.copy_(self.y_host[lo:lo + self.batch_size], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
         return dx, dy, ev
@@ -281,10 +292,11 @@ class PinnedHostLoader:
     def next(self) -> Tuple[torch.Tensor, torch.Tensor]:
         """Returns this step's batch (its H2D copy was enqueued one call earlier, so it overlaps the previous step's
         compute) and enqueues the copy of the following one.  Every step still moves its own inputs host->device."""
-        if self._pending is None:
-            self._pending = self._issue()
-        dx, dy, ev = self._pending
+        while len(self._pending) < self.depth - 1:
+            self._pending.append(self._issue())
+        dx, dy, ev = self._pending.pop(0)
         if ev is not None:
             torch.cuda.current_stream(self.device).wait_event(ev)
-        self._pending = self._issue()
+        # refill: the slot this copy overwrites was handed out depth - 1 calls ago; the step that consumed it is enqueued
+        self._pending.append(self._issue())
         return dx, dy

@@ -72,6 +72,8 @@ class TrainEngine:
                                                          and cfg.grad_buckets) else None
         self._graph = None
         self._static = None
+        self._bound = {}                        # (x ptr, y ptr, shape) -> (graph captured on that buffer, its loss tensor)
+        self._bound_keepalive = []
         self.steps_done = 0
 
     # ---------------------------------------------------------------------------------------------------
@@ -157,12 +159,24 @@ class TrainEngine:
         self.steps_done += 1
         if self._graph is None:
             return self._step_eager(x, y)
-        sx, sy, sloss = self._static
-        sx.copy_(x, non_blocking=True)
-        sy.copy_(y, non_blocking=True)
-        self._graph.replay()
+        bound = self._bound.get((x.data_ptr(), y.data_ptr(), tuple(x.shape)))
+        if bound is not None:                   # the batch already sits in a buffer a graph was captured on: no staging copy
+            g, sloss = bound
+        else:
+            sx, sy, sloss = self._static
+            if x.data_ptr() != sx.data_ptr():       # (a loader may have gathered the batch straight into graph_inputs())
+                sx.copy_(x, non_blocking=True)
+            if y.data_ptr() != sy.data_ptr():
+                sy.copy_(y, non_blocking=True)
+            g = self._graph
+        g.replay()
         self.optimizer.step_count += 1          # host mirror; the kernels use the device-resident counter
         return sloss
+
+    def graph_inputs(self):
+        """(x, y) input buffers of the captured graph, or None: a loader that assembles batches on the device can write them
+        here directly (``DeviceShard.next(out=...)``) and ``step()`` then skips its staging copy."""
+        return None if self._graph is None else self._static[:2]
 
     def maybe_average(self, force: bool = False):
         """Parameter-average sync point (reference semantics: once, at the end; or every ``sync_every`` steps)."""
@@ -173,9 +187,14 @@ class TrainEngine:
             self.comm.average_params_(self.flat, cfg.average_scope)
 
     # ---------------------------------------------------------------------------------------------------
-    def capture(self, x: torch.Tensor, y: torch.Tensor, warmup: int = 3):
+    def capture(self, x: torch.Tensor, y: torch.Tensor, warmup: int = 3, bind=()):
         """Capture fwd+bwd+update into one CUDA graph (static shapes).  Adam's bias correction is derived in-kernel from
-        a device-resident step counter, so replays are exact."""
+        a device-resident step counter, so replays are exact.
+
+        ``bind``: ``(x, y)`` pairs of LONG-LIVED device buffers that batches will be handed over in (the two staging slots of
+        ``PinnedHostLoader``, fixed slices of a device-resident shard).  One more graph is captured directly on each of them,
+        and ``step()`` replays it when it is given exactly that buffer - the 67 MB copy into the graph's own input buffer
+        (27 us of a 4 ms step) disappears.  Any other tensor still goes through the staging copy."""
         assert self.device.type == "cuda"
         sx, sy = x.clone(), y.clone()
         # warm-up / capture run real updates: snapshot the training state and put it back, so capturing is not
@@ -193,6 +212,14 @@ class TrainEngine:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             sloss = self._step_eager(sx, sy)
+        bound = {}
+        for bx, by in bind:
+            assert bx.shape == sx.shape and bx.dtype == sx.dtype and by.shape == sy.shape and bx.is_contiguous() and by.is_contiguous()
+            gb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gb):
+                lb = self._step_eager(bx, by)
+            bound[(bx.data_ptr(), by.data_ptr(), tuple(bx.shape))] = (gb, lb)
+            self._bound_keepalive.append((bx, by))          # the graphs hold raw pointers into these buffers
         with torch.no_grad():
             self.flat.data.copy_(snap["data"])
             self.flat.refresh_shadow()
@@ -201,7 +228,7 @@ class TrainEngine:
             if snap["step_dev"] is not None:
                 opt.step_dev.copy_(snap["step_dev"])
             opt.step_count = snap["step_count"]
-        self._graph, self._static = g, (sx, sy, sloss)
+        self._graph, self._static, self._bound = g, (sx, sy, sloss), bound
         return g
 
     @torch.no_grad()

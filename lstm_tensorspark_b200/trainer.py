@@ -182,7 +182,9 @@ def train_rnn(partition, cfg: Config, rank: int = 0, world_size: int = 1, comm: 
             sys.stderr.write(f"{tag} - fault injected on rank {rank} at step {step}\n")
             sys.stderr.flush()
             os._exit(17)
-        train_input, train_labels = loader.next()
+        # with a captured step the batch is gathered straight into the graph's input buffers (no second copy)
+        gi = eng.graph_inputs() if isinstance(loader, D.DeviceShard) else None
+        train_input, train_labels = loader.next(out=gi) if gi is not None else loader.next()
 
         with M.nvtx_range("step", cfg.nvtx):
             if cfg.cuda_graph and device.type == "cuda" and eng._graph is None and step == start_step + 3:

@@ -126,3 +126,15 @@ def test_pinned_loader_yields_batches_in_order_cpu():
     seen = [pl.next()[1].clone().numpy() for _ in range(7)]       # crosses an epoch boundary (5 batches per pass)
     assert [int(b[0]) for b in seen] == [0, 8, 16, 24, 32, 0, 8]
     assert all(len(b) == 8 for b in seen)
+
+
+def test_pinned_loader_depth_three_same_order_cpu():
+    x = np.arange(40 * 3, dtype=np.float32).reshape(40, 3)
+    y = np.arange(40, dtype=np.int64)
+    pl = D.PinnedHostLoader(x, y, 8, "cpu", shuffle=False, depth=3)
+    seen = []
+    for _ in range(7):
+        xb, yb = pl.next()
+        assert np.allclose(xb.numpy(), x[int(yb[0]):int(yb[0]) + 8])   # the slot still holds ITS batch when it is handed out
+        seen.append(int(yb[0]))
+    assert seen == [0, 8, 16, 24, 32, 0, 8] and len(pl.dev) == 3

@@ -88,6 +88,25 @@ def test_sequence_job_grad_allreduce_and_resume(tmp_path):
     assert all(torch.equal(v0[k], v1[k]) for k in v0) and torch.equal(o0["optimizer"]["m"], o1["optimizer"]["m"])
 
 
+def test_trainer_cuda_graph_matches_eager(tmp_path):
+    """`--cuda_graph true` on one GPU: the step is captured after 3 eager steps and the batches are gathered straight into the
+    graph's input buffers from then on; the run ends with the same weights and optimizer state as the eager run."""
+    def common(ck, graph):
+        return ["rnn.py", "--synthetic", "1024", "--seq_len", "8", "--in_features", "64", "--hidden_units", "128,128",
+                "--batch_size", "128", "--num_classes", "10", "--partitions", "1", "--init", "scaled", "--learn_initial_state", "false",
+                "--deterministic", "true", "--cuda_graph", graph, "--max_steps", "10", "--evaluate_every", "5",
+                "--checkpoint_path", str(tmp_path / ck), "--output_path", str(tmp_path / (ck + "_out")), "--quiet"]
+    _run(common("e", "false"))
+    _run(common("g", "true"))
+    ve, me, oe = _final(str(tmp_path / "e"), sorted(os.listdir(tmp_path / "e"))[0], 0)
+    vg, mg, og = _final(str(tmp_path / "g"), sorted(os.listdir(tmp_path / "g"))[0], 0)
+    assert me["global_step"] == mg["global_step"] == 9
+    assert oe["optimizer"]["step"] == og["optimizer"]["step"] == 10
+    for k in ve:
+        assert torch.allclose(ve[k].float(), vg[k].float(), rtol=1e-4, atol=1e-6), (k, float((ve[k].float() - vg[k].float()).abs().max()))
+    assert torch.allclose(oe["optimizer"]["m"], og["optimizer"]["m"], rtol=1e-4, atol=1e-8) and oe["loader"]["i"] == og["loader"]["i"]
+
+
 def test_fused_comm_dead_peer_is_an_error_not_a_hang(tmp_path):
     """--fault_inject on GPUs: rank 1 dies at step 3; the surviving rank's in-kernel cross-GPU barrier times out (bounded
     spin -> sticky error flag) or the launcher sees the exit code first - either way the job fails fast with rank 1's code."""

@@ -136,3 +136,46 @@ def test_layer_wavefront_matches_sequential_layers():
     assert cuda_lstm.STATS.get("wavefront_fwd", 0) == n0 + 1
     for i, (g, r) in enumerate(zip(got, ref)):
         assert _rel_l2(g, r) <= 5e-3, (i, tuple(r.shape), _rel_l2(g, r))
+
+
+def test_graphs_bound_to_input_buffers_match_the_eager_step():
+    """`TrainEngine.capture(bind=...)`: a step replayed from a graph captured directly on the buffer the batch arrives in (no
+    staging copy), from the staged graph (any other tensor) and the eager step walk the same trajectory (Adam, lr > 0)."""
+    from lstm_tensorspark_b200.config import Config
+    from lstm_tensorspark_b200.engine import TrainEngine
+    from lstm_tensorspark_b200 import data as Dm
+    from lstm_tensorspark_b200.ops import cuda_lstm
+    dev = torch.device("cuda", 0)
+    T, B, D, C = 8, 256, 128, 10
+
+    def mk():
+        torch.manual_seed(11)
+        cfg = Config(partitions=1, sync_mode="none", init="scaled", learn_initial_state=False, device="cuda", quiet=True,
+                     learning_rate=1e-3, hidden_units="256,256", in_features=D, seq_len=T, batch_size=B, num_classes=C, seed=11)
+        return TrainEngine(cfg, 0, 1, None, batch_size=B, device=dev, dtype=torch.bfloat16)
+
+    xs, ys = Dm.synthetic_sequences(3 * B, T, D, C, seed=2)
+    xs = torch.as_tensor(xs).to(dev).bfloat16()
+    ys = torch.as_tensor(ys).to(dev)
+    batches = [(xs[i * B:(i + 1) * B], ys[i * B:(i + 1) * B]) for i in range(3)]
+    order = [0, 1, 2, 1, 0, 2]
+    eager = mk()
+    want = [float(eager.step(*batches[i])) for i in order]
+    graphed = mk()
+    with torch.no_grad():
+        assert torch.equal(graphed.flat.data, mk().flat.data)             # same seed -> same initial weights
+    graphed.capture(*batches[0], bind=batches[1:])                       # batch 0: staged path; batches 1, 2: bound graphs
+    assert len(graphed._bound) == 2
+    staging_before = graphed._static[0].clone()
+    got = []
+    for i in order:
+        got.append(float(graphed.step(*batches[i])))
+        if i != 0:
+            assert torch.equal(graphed._static[0], staging_before)        # a bound replay never touches the staging buffer
+        else:
+            staging_before = graphed._static[0].clone()
+    for a, b in zip(got, want):
+        assert abs(a - b) <= 2e-3 * max(1.0, abs(b)), (got, want)
+    assert _rel_l2(graphed.flat.data, eager.flat.data) < 1e-3
+    assert graphed.optimizer.step_count == eager.optimizer.step_count == len(order)
+    cuda_lstm.check_kernel_errors(dev)

@@ -80,3 +80,24 @@ def test_bucket_queue_never_releases_a_dependent_of_its_own_producer():
     CL.queue_after_big_launch(lambda: fired.append("last"))
     CL._after_big_launch(flush=True)                    # end of backward: whatever is left goes in stream order
     assert fired[-1] == "last" and not CL.AFTER_SEQ_BWD
+
+
+def test_device_shard_gathers_into_given_buffers():
+    """`DeviceShard.next(out=...)` (the trainer hands it the captured graph's input buffers) yields the same batches as `next()`."""
+    import numpy as np
+    import torch
+    from lstm_tensorspark_b200 import data as D
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((40, 3, 5)).astype(np.float32)
+    y = rng.integers(0, 4, size=40).astype(np.int64)
+    a = D.DeviceShard(x, y, 8, "cpu", dtype=torch.float32, shuffle=True, seed=3)
+    b = D.DeviceShard(x, y, 8, "cpu", dtype=torch.float32, shuffle=True, seed=3)
+    xb, yb = torch.empty(8, 3, 5), torch.empty(8, dtype=torch.int64)
+    for _ in range(12):                                   # crosses two reshuffles
+        xa, ya = a.next()
+        xo, yo = b.next(out=(xb, yb))
+        assert xo.data_ptr() == xb.data_ptr() and torch.equal(xa, xo) and torch.equal(ya, yo)
+    wrong = (torch.empty(4, 3, 5), torch.empty(4, dtype=torch.int64))      # wrong batch size: falls back to fresh tensors
+    xa, _ = a.next()
+    xo, _ = b.next(out=wrong)
+    assert torch.equal(xa, xo) and xo.data_ptr() != wrong[0].data_ptr()
