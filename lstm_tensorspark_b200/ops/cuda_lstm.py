@@ -1,10 +1,13 @@
-"""CUDA LSTM layer op = autograd.Function around the hand-written kernels.
+"""CUDA LSTM layer ops = autograd.Functions around the hand-written kernels.
 
-Fast path (bf16, H % 64 == 0, grid <= #SMs): hoisted input projection on the tcgen05 GEMM (csrc/gemm_tcgen05.cu) + ONE
+Fast path (bf16, H % 64 == 0, grid <= #SMs): hoisted input projection on the tcgen05 GEMM (csrc/gemm2_tcgen05.cu) + ONE
 persistent tcgen05 kernel for the whole recurrence in each direction (csrc/lstm_seq_tcgen05.cu; weights resident in SMEM
-up to H = 1024, streamed through the ring above).  Generic path (any shape / fp32): library GEMM per step + the fused pointwise cell
-kernels (csrc/lstm_pointwise.cu).  Weight gradients are plain library GEMMs over all T at once
-(``[4H, T·B] x [T·B, D+H]``), fp32 output.  Math parity: /root/reference/src/models/recurrent/lstm.py:88-122.
+up to H = 1024, streamed through the ring above).  Two stacked layers run as ONE layer wavefront (``_LSTMPairFn``: both
+recurrences co-resident, the upper layer's x-projection / dX as a dataflow-gated GEMM on the idle SMs).  Generic path (any
+shape / fp32): our CUDA-core GEMM per step (csrc/gemm_generic.cu) + the fused pointwise cell kernels (csrc/lstm_pointwise.cu).
+Weight gradients are tcgen05 GEMMs over all T at once (``[4H, T·B] x [T·B, D | H]``, both operands MN-major and read in
+place), fp32, written straight into the flat gradient buffer; bias gradients are deterministic column sums running next to
+them.  Nothing in here reaches cuBLAS / cuDNN.  Math parity: /root/reference/src/models/recurrent/lstm.py:88-122.
 """
 from __future__ import annotations
 
@@ -25,8 +28,6 @@ FORCE_GENERIC = os.environ.get("LSTM_TS_FORCE_GENERIC", "0") == "1"
 #   6 no L2 prefetch, 7 cluster-scope acquire on the exchange barriers), [16:18) sync mode (0 per-k-block dataflow counters,
 #   1 one counter per batch tile = grid barrier, 2 per-CTA flags), bit 18 acquire polls, bit 19 no forward K-split.
 SEQ_VARIANT = int(os.environ.get("LSTM_TS_SEQ_VARIANT", "0"))
-USE_TC_GEMM = os.environ.get("LSTM_TS_TC_GEMM", "1") == "1"
-GEMM_VARIANT = int(os.environ.get("LSTM_TS_GEMM_VARIANT", "1"))   # 0: 128x128 tiles, 1: 128x256 tiles (faster on large shapes)
 STATS = {"fast_fwd": 0, "fast_bwd": 0, "generic_fwd": 0, "generic_bwd": 0, "tc_gemm": 0, "kernels": 0}
 
 
