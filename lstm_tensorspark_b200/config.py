@@ -58,6 +58,9 @@ class Config:
     synthetic: int = 0                  # >0: use N synthetic sequences instead of a CSV
     remainder: str = "drop"             # drop | spread : rows beyond floor(N/P)*P (Q2)
     cuda_graph: bool = False
+    data_residency: str = "device"      # device: the shard lives in HBM, a batch is an on-device gather (no per-step H2D) |
+                                        # host: the shard stays in pinned host memory and every batch is copied host->device by an
+                                        # asynchronous, triple-buffered DMA (the reference's per-step feed, src/rnn.py:264-267; shards > HBM)
     trace: str = ""                     # path for a torch.profiler chrome trace
     nvtx: bool = False
     json_log: str = ""                  # machine readable metrics file
@@ -119,6 +122,8 @@ class Config:
             raise ValueError(f"unknown --average_scope {self.average_scope}")
         if self.steps_mode not in ("compat", "epochs"):
             raise ValueError(f"unknown --steps_mode {self.steps_mode}")
+        if self.data_residency not in ("device", "host"):
+            raise ValueError(f"unknown --data_residency {self.data_residency}")
         if self.remainder not in ("drop", "spread"):
             raise ValueError(f"unknown --remainder {self.remainder}")
         if self.mode != "train":

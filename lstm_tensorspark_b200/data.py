@@ -247,6 +247,15 @@ class PinnedHostLoader:
         self._copy_stream = None
         self.debug_skip_copy = False
         self._i = self.per_epoch if shuffle else 0
+        # resume bookkeeping: `_order` = which original row sits in each row of the (in-place permuted) pinned arrays; per pass
+        # the generator state and order from BEFORE that pass's shuffle (the last two passes: prefetched batches may already
+        # belong to the next one); `_consumed` = (pass, batches handed out in it)
+        self._order = torch.arange(self.n)
+        self._pass = 0 if shuffle else 1
+        self._pass_start = {}
+        if not shuffle:
+            self._pass_start[1] = (self.gen.get_state(), self._order.clone())
+        self._consumed = (self._pass, 0)
         self.bytes_per_batch = self.dev[0][0].numel() * self.dev[0][0].element_size() + self.batch_size * 8
 
     def _reshuffle(self):
@@ -254,13 +263,22 @@ class PinnedHostLoader:
         # it must not read pinned memory that is being re-permuted underneath it
         if self._copy_stream is not None:
             self._copy_stream.synchronize()
+        # a pass is ``original[randperm]`` - the same batches DeviceShard draws from the same seed - so the rows that are
+        # already permuted in place have to be addressed through the inverse of the current order
         perm = torch.randperm(self.n, generator=self.gen)
-        xs, ys = self.x_host[perm], self.y_host[perm]
+        inv = torch.empty_like(self._order)
+        inv[self._order] = torch.arange(self.n)
+        idx = inv[perm]
+        xs, ys = self.x_host[idx], self.y_host[idx]
         self.x_host.copy_(xs)
         self.y_host.copy_(ys)
+        self._order = perm
 
     def _advance(self) -> int:
         if self._i >= self.per_epoch:
+            self._pass += 1
+            self._pass_start[self._pass] = (self.gen.get_state(), self._order.clone())
+            self._pass_start.pop(self._pass - self.depth - 1, None)     # (a tiny shard can be prefetched several passes ahead)
             if self.shuffle:
                 self._reshuffle()
             self._i = 0
@@ -268,15 +286,43 @@ class PinnedHostLoader:
         self._i += 1
         return lo
 
+    def state_dict(self):
+        """Position of the NEXT batch to be handed out (prefetched-but-unconsumed batches are not counted), exact across a
+        reshuffle: generator state and row order from before the shuffle of the pass that batch belongs to."""
+        ps, k = self._consumed
+        if k >= self.per_epoch or ps not in self._pass_start:      # the next batch opens a new pass
+            if ps + 1 in self._pass_start:
+                ps, k = ps + 1, 0
+            else:                                                  # ... which has not been prefetched yet: current state is its start
+                return {"gen": self.gen.get_state(), "order": self._order.clone(), "i": 0, "shuffle_first": self.shuffle, "pinned": True}
+        gen, order = self._pass_start[ps]
+        return {"gen": gen, "order": order.clone(), "i": k, "shuffle_first": self.shuffle, "pinned": True}
+
+    def load_state_dict(self, st):
+        """Call on a freshly constructed loader over the same arrays (rows in their original order)."""
+        assert not self._pending and int(self._order[0]) == 0 and bool((self._order[1:] > self._order[:-1]).all())
+        order = st["order"]
+        self.x_host.copy_(self.x_host[order])
+        self.y_host.copy_(self.y_host[order])
+        self._order = order.clone()
+        self.gen.set_state(st["gen"])
+        self._pass = 0
+        self._pass_start = {}
+        self._i = self.per_epoch                     # the first _advance() opens pass 1: records its start, shuffles, ...
+        self._advance()
+        self._i = st["i"]                            # ... and the batches already consumed in it are skipped
+        self._consumed = (self._pass, st["i"])
+
     def _issue(self):
         """Enqueue the H2D copy of the next batch on the copy stream into the free staging slot."""
         lo = self._advance()
+        tag = (self._pass, self._i)                      # handing this batch out makes it the consumed position
         dx, dy = self.dev[self._slot]
         self._slot = (self._slot + 1) % self.depth
         if self.device.type != "cuda":
             dx.copy_(self.x_host[lo:lo + self.batch_size])
             dy.copy_(self.y_host[lo:lo + self.batch_size])
-            return dx, dy, None
+            return dx, dy, None, tag
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         # the slot being overwritten was consumed by compute work already enqueued on the current stream
@@ -287,14 +333,14 @@ class PinnedHostLoader:
                 dy.copy_(self.y_host[lo:lo + self.batch_size], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
-        return dx, dy, ev
+        return dx, dy, ev, tag
 
     def next(self) -> Tuple[torch.Tensor, torch.Tensor]:
         """Returns this step's batch (its H2D copy was enqueued one call earlier, so it overlaps the previous step's
         compute) and enqueues the copy of the following one.  Every step still moves its own inputs host->device."""
         while len(self._pending) < self.depth - 1:
             self._pending.append(self._issue())
-        dx, dy, ev = self._pending.pop(0)
+        dx, dy, ev, self._consumed = self._pending.pop(0)
         if ev is not None:
             torch.cuda.current_stream(self.device).wait_event(ev)
         # refill: the slot this copy overwrites was handed out depth - 1 calls ago; the step that consumed it is enqueued

@@ -126,8 +126,13 @@ def train_rnn(partition, cfg: Config, rank: int = 0, world_size: int = 1, comm: 
     sink = M.SummarySink(os.path.join(model_save_dir, "train"))
     jlog = M.JsonLog(cfg.json_log)
 
-    loader = D.DeviceShard(train_x, train_y, batch_size, device, dtype=torch.float32, shuffle=True,
-                           seed=cfg.seed + 17 * (rank + 1))
+    if cfg.data_residency == "host":
+        # the reference's feed (src/rnn.py:264-267: every batch travels host -> device), as an asynchronous DMA pipeline
+        loader = D.PinnedHostLoader(train_x, train_y, batch_size, device, dtype=torch.float32, shuffle=True,
+                                    seed=cfg.seed + 17 * (rank + 1), depth=3)
+    else:
+        loader = D.DeviceShard(train_x, train_y, batch_size, device, dtype=torch.float32, shuffle=True,
+                               seed=cfg.seed + 17 * (rank + 1))
     start_step = 0
     if cfg.resume or cfg.use_pretrained_model:
         src = cfg.resume or ckpt.find_latest_run(cfg.checkpoint_path, None if standalone else str(partition_key))
@@ -142,7 +147,11 @@ def train_rnn(partition, cfg: Config, rank: int = 0, world_size: int = 1, comm: 
             if opt_state is not None:
                 comm.load_optimizer_state(optimizer, opt_state["optimizer"])
                 if opt_state.get("loader") is not None:
-                    loader.load_state_dict(opt_state["loader"])      # continue the data order, do not replay it
+                    st = opt_state["loader"]
+                    if bool(st.get("pinned")) == isinstance(loader, D.PinnedHostLoader):
+                        loader.load_state_dict(st)                   # continue the data order, do not replay it
+                    else:
+                        sys.stderr.write(f"{tag} - checkpoint was written with another --data_residency: data order starts over\n")
             start_step = int(meta.get("global_step", -1)) + 1
             if not cfg.quiet:
                 print(f"{tag} - restored {src} (resuming at step {start_step})")
@@ -188,7 +197,8 @@ def train_rnn(partition, cfg: Config, rank: int = 0, world_size: int = 1, comm: 
 
         with M.nvtx_range("step", cfg.nvtx):
             if cfg.cuda_graph and device.type == "cuda" and eng._graph is None and step == start_step + 3:
-                eng.capture(train_input, train_labels)          # static shapes: replay the captured step from here on
+                # static shapes: replay the captured step from here on (host feed: one graph per staging slot, no extra copy)
+                eng.capture(train_input, train_labels, bind=list(loader.dev) if isinstance(loader, D.PinnedHostLoader) else ())
             loss = eng.step(train_input, train_labels)
         samples += batch_size
 

@@ -2,6 +2,7 @@
 flag defaults, net_settings)."""
 import numpy as np
 import pytest
+import torch
 
 from lstm_tensorspark_b200 import data as D
 from lstm_tensorspark_b200.config import Config, parse_args
@@ -138,3 +139,28 @@ def test_pinned_loader_depth_three_same_order_cpu():
         assert np.allclose(xb.numpy(), x[int(yb[0]):int(yb[0]) + 8])   # the slot still holds ITS batch when it is handed out
         seen.append(int(yb[0]))
     assert seen == [0, 8, 16, 24, 32, 0, 8] and len(pl.dev) == 3
+
+
+@pytest.mark.parametrize("depth,per_pass", [(2, 5), (3, 5), (3, 2), (4, 1)])
+def test_pinned_loader_resume_is_exact(depth, per_pass):
+    """state_dict() = position of the next batch to be handed out, whatever has been prefetched (also across reshuffles and
+    when the prefetch runs more than one pass ahead of a tiny shard): a fresh loader continues with exactly the same batches."""
+    bs = 8
+    n = bs * per_pass
+    x = np.arange(n * 3, dtype=np.float32).reshape(n, 3)
+    y = np.arange(n, dtype=np.int64)
+    mk = lambda: D.PinnedHostLoader(x.copy(), y.copy(), bs, "cpu", shuffle=True, seed=5, depth=depth)
+    ref = mk()
+    want = [ref.next()[1].clone() for _ in range(14)]
+    for k in (0, 1, per_pass, per_pass + 1, 2 * per_pass, 7):
+        a = mk()
+        for j in range(k):
+            assert torch.equal(a.next()[1], want[j])
+        st = a.state_dict()
+        b = mk()
+        b.load_state_dict(st)
+        for j in range(k, 14):
+            xb, yb = b.next()
+            assert torch.equal(yb, want[j]), (depth, per_pass, k, j)
+            assert np.allclose(xb.numpy(), x[yb.numpy()])                       # rows and labels stay together
+        assert b.state_dict()["i"] == ref.state_dict()["i"]

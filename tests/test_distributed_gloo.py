@@ -119,3 +119,17 @@ def test_oversubscription_needs_the_one_shot_average(tmp_path, iris_path):
     cfg = _cfg(tmp_path, iris_path, partitions=4, max_workers=2, sync_mode="grad_allreduce")
     with pytest.raises(ValueError):
         run_job(cfg, standalone=False)
+
+
+def test_host_resident_feed_matches_the_device_resident_one(tmp_path, iris_path):
+    """--data_residency host (pinned host shard, every batch copied to the device by the prefetch pipeline - the reference's
+    per-step feed) draws the same batches as the device-resident gather: two ranks, per-step gradient allreduce, same result."""
+    outs = {}
+    for res in ("device", "host"):
+        cfg = _cfg(tmp_path / res, iris_path, sync_mode="grad_allreduce", average_scope="all", max_steps=6, batch_size=15,
+                   data_residency=res, evaluate_every=5)
+        out = run_job(cfg, standalone=False)
+        outs[res] = [r["loss"] for r in out["results"]]
+        assert out["world_size"] == 2 and all(r["steps"] == 6 for r in out["results"])
+    # both loaders permute a pass with torch.randperm from the same seeded generator -> identical batches -> identical losses
+    assert outs["device"] == pytest.approx(outs["host"], rel=1e-6)

@@ -95,10 +95,13 @@ def _final_state(cfg):
     return ckpt.load(ckpt.latest_checkpoint(d))
 
 
-def test_resume_is_equivalent_to_an_uninterrupted_run(tmp_path, iris_path):
+@pytest.mark.parametrize("residency,bs,steps", [("device", 10, 8), ("host", 10, 8), ("host", 60, 8)])
+def test_resume_is_equivalent_to_an_uninterrupted_run(tmp_path, iris_path, residency, bs, steps):
     """8 steps straight == 4 steps + resume + 4 steps, bit for bit: weights, Adam slots, step counter AND the position in
-    the data order (the loader state is restored, not replayed from the first permutation)."""
-    common = dict(evaluate_every=1, learning_rate=1e-2)
+    the data order (the loader state is restored, not replayed from the first permutation).  ``host``: the pinned-memory feed
+    with its prefetched-but-unconsumed batches; batch 60 of 150 rows = 2 batches per pass, so the resume point sits on a
+    reshuffle boundary that the prefetch has already crossed."""
+    common = dict(evaluate_every=1, learning_rate=1e-2, data_residency=residency, batch_size=bs)
     a = _cfg(tmp_path / "a", iris_path, max_steps=8, **common)
     run_job(a, standalone=True)
     va, ma, oa = _final_state(a)
@@ -113,4 +116,5 @@ def test_resume_is_equivalent_to_an_uninterrupted_run(tmp_path, iris_path):
         assert torch.equal(va[k], vb[k]), k
     assert oa["optimizer"]["step"] == ob["optimizer"]["step"] == 8
     assert torch.equal(oa["optimizer"]["m"], ob["optimizer"]["m"]) and torch.equal(oa["optimizer"]["v"], ob["optimizer"]["v"])
-    assert oa["loader"]["i"] == ob["loader"]["i"] and torch.equal(oa["loader"]["perm"], ob["loader"]["perm"])
+    key = "perm" if residency == "device" else "order"
+    assert oa["loader"]["i"] == ob["loader"]["i"] and torch.equal(oa["loader"][key], ob["loader"][key])
