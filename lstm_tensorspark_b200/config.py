@@ -126,8 +126,9 @@ class Config:
             raise ValueError(f"unknown --data_residency {self.data_residency}")
         if self.remainder not in ("drop", "spread"):
             raise ValueError(f"unknown --remainder {self.remainder}")
-        if self.mode != "train":
-            raise ValueError("only --mode train is implemented (as in the reference, src/rnn.py:371)")
+        if self.mode not in ("train", "eval"):
+            raise ValueError("--mode is train (the only one the reference implements, src/rnn.py:371) or eval (score a trained "
+                             "model: --resume <averaged_model.pt | checkpoint dir>, default = what the last training run left)")
         return self
 
 

@@ -342,8 +342,83 @@ def load_shards(cfg: Config, world_size: int, standalone: bool):
     return D.text_to_partitions(cfg.training_path, world_size, shuffle=True, seed=cfg.seed, remainder=cfg.remainder)
 
 
+def _find_trained_model(cfg: Config, standalone: bool):
+    """--resume <file | dir>, else <output_path>/averaged_model.pt (distributed job), else the latest checkpoint under
+    --checkpoint_path.  -> (variables in the reference's names, description)."""
+    src = cfg.resume
+    if not src and not standalone and cfg.output_path and os.path.isfile(os.path.join(cfg.output_path, "averaged_model.pt")):
+        src = os.path.join(cfg.output_path, "averaged_model.pt")
+    if not src:
+        src = ckpt.find_latest_run(cfg.checkpoint_path, None if standalone else "0")
+    if src and os.path.isdir(src) and os.path.isfile(os.path.join(src, "averaged_model.pt")):
+        src = os.path.join(src, "averaged_model.pt")
+    if src and os.path.isfile(src) and src.endswith(".pt"):
+        blob = torch.load(src, map_location="cpu", weights_only=False)
+        return blob["variables"], src
+    if src and os.path.isdir(src):
+        if ckpt.latest_checkpoint(src) is None and os.path.isdir(os.path.join(src, "0")):
+            src = os.path.join(src, "0")
+        last = ckpt.latest_checkpoint(src)
+        if last:
+            return ckpt.load(last)[0], last
+    raise FileNotFoundError("--mode eval: no trained model found (give --resume <averaged_model.pt | checkpoint dir>)")
+
+
+def evaluate_job(cfg: Config, standalone: bool = False) -> Dict:
+    """``--mode eval``: score a trained model on ``--training_path`` (or ``--synthetic``) - loss and accuracy over the whole
+    file in batches of ``--batch_size``, forward kernels only, one device.  Not in the reference (its ``--mode`` flag knows
+    only ``train`` and the averaged model is thrown away, src/rnn.py:371,407-408); it closes the train -> average -> use loop."""
+    from .engine import TrainEngine
+    variables, src = _find_trained_model(cfg, standalone)
+    if cfg.synthetic:
+        x, y = D.synthetic_sequences(cfg.synthetic, cfg.seq_len, cfg.in_features, cfg.num_classes, seed=cfg.seed)
+    else:
+        rows = D.read_dataset_from_path(cfg.training_path)
+        x, y = D.process_batch(rows, normalize=cfg.normalize, seq_len=cfg.seq_len, in_features=cfg.in_features)
+    device = resolve_device(cfg, 0)
+    dtype = resolve_dtype(cfg, device)
+    F.set_backend(cfg.backend if cfg.backend != "auto" else "auto")
+    n = x.shape[0]
+    bs = D.resolve_batch_size(cfg.batch_size if cfg.batch_size and cfg.batch_size <= n else 0, n)
+    eng = TrainEngine(cfg, 0, 1, Communicator(0, 1), batch_size=bs, device=device, dtype=dtype)
+    # the reference's trainable initial state is one row PER BATCH ROW ([batch_size, H], src/models/recurrent/lstm.py:24-33):
+    # scoring with another batch size uses the mean learned row for every sample
+    shapes = {k: tuple(v.shape) for k, v in eng.model.named_reference_variables()}
+    variables = dict(variables)
+    for k, v in list(variables.items()):
+        want = shapes.get(k)
+        if want is not None and tuple(v.shape) != want and v.dim() == 2 and len(want) == 2 and v.shape[1] == want[1]:
+            variables[k] = v.float().mean(0, keepdim=True).expand(want).contiguous()
+    eng.model.load_reference_state_dict(variables, strict=False)
+    eng.flat.refresh_shadow()
+    xs = torch.as_tensor(x).to(device=device, dtype=torch.float32)
+    ys = torch.as_tensor(y).to(device)
+    loss_sum, correct, seen = 0.0, 0.0, 0
+    start = time.time()
+    for lo in range(0, n - bs + 1, bs):                 # full batches (static shapes for the kernels); the tail is scored below
+        l, a = eng.evaluate(xs[lo:lo + bs], ys[lo:lo + bs])
+        loss_sum += float(l) * bs; correct += float(a) * bs; seen += bs
+    if seen < n:                                        # remainder: the last `bs` rows, counting only the ones not seen yet
+        from .ops import reference as ref
+        with torch.no_grad():
+            logits = eng.model.head(eng.model.features(xs[n - bs:]))[bs - (n - seen):]
+        tail_y = ys[seen:]
+        loss_sum += float(ref.softmax_xent(logits.float(), tail_y)) * (n - seen)
+        correct += float(ref.accuracy(logits.float(), tail_y)) * (n - seen)
+        seen = n
+    out = {"mode": "eval", "model": src, "samples": seen, "loss": loss_sum / seen, "accuracy": correct / seen,
+           "seconds": time.time() - start}
+    if not cfg.quiet:
+        print("RNN-LSTM - eval: model {model}, {samples} samples, loss {loss:.6f}, accuracy {accuracy:.4f}".format(**out))
+    if cfg.json_log:
+        jl = M.JsonLog(cfg.json_log); jl.write(**out); jl.close()
+    return out
+
+
 def run_job(cfg: Config, standalone: bool = False) -> Dict:
     """``main`` of both entry points: shard -> N replicas -> average -> output."""
+    if cfg.mode == "eval":
+        return evaluate_job(cfg, standalone)
     from .parallel.launch import launch, in_torchrun
     world_size = resolve_workers(cfg, standalone)
     if in_torchrun():

@@ -118,3 +118,25 @@ def test_resume_is_equivalent_to_an_uninterrupted_run(tmp_path, iris_path, resid
     assert torch.equal(oa["optimizer"]["m"], ob["optimizer"]["m"]) and torch.equal(oa["optimizer"]["v"], ob["optimizer"]["v"])
     key = "perm" if residency == "device" else "order"
     assert oa["loader"]["i"] == ob["loader"]["i"] and torch.equal(oa["loader"][key], ob["loader"][key])
+
+
+def test_mode_eval_scores_a_trained_model(tmp_path, iris_path):
+    """--mode eval: the checkpoint a standalone run left / an averaged model of a distributed run is scored on the whole file
+    (full batches + the remainder), and a trained model beats an untrained one."""
+    from lstm_tensorspark_b200.ops import reference as ref
+    cfg = _cfg(tmp_path, iris_path, epochs=6, learning_rate=2e-2)
+    run_job(cfg, standalone=True)
+    ev = run_job(_cfg(tmp_path, iris_path, mode="eval", batch_size=40), standalone=True)       # 150 rows: 3 full batches + 30
+    assert ev["mode"] == "eval" and ev["samples"] == 150 and 0.0 < ev["loss"] < 1.0 and ev["accuracy"] > 0.45
+    whole = run_job(_cfg(tmp_path, iris_path, mode="eval", batch_size=0), standalone=True)      # one batch = the whole file
+    assert whole["samples"] == 150 and abs(whole["loss"] - ev["loss"]) < 1e-5 and abs(whole["accuracy"] - ev["accuracy"]) < 1e-6
+    # distributed job -> <output_path>/averaged_model.pt -> eval picks it up
+    d = Config(training_path=iris_path, hidden_units="16", checkpoint_path=str(tmp_path / "ck2"), partitions=2, comm="gloo",
+               output_path=str(tmp_path / "out2"), device="cpu", quiet=True, epochs=2, sync_mode="grad_allreduce",
+               average_scope="all", learning_rate=2e-2, timeout_s=120).validate()
+    run_job(d, standalone=False)
+    d.mode = "eval"
+    ev2 = run_job(d.validate(), standalone=False)
+    assert ev2["model"].endswith("averaged_model.pt") and ev2["samples"] == 150 and ev2["accuracy"] > 0.4
+    with pytest.raises(FileNotFoundError):
+        run_job(_cfg(tmp_path / "none", iris_path, mode="eval"), standalone=True)
