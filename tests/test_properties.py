@@ -68,3 +68,36 @@ def test_flat_params_layout_is_aligned_and_aliasing(shapes):
         off += p.numel()
     flat.data.zero_()
     assert all(float(p.detach().abs().sum()) == 0.0 for p in params)     # parameters are views of the flat buffer
+
+
+@settings(max_examples=40, deadline=None)
+@given(depth=st.integers(2, 5), per_pass=st.integers(1, 6), bs=st.integers(1, 5), extra=st.integers(0, 3), stop=st.integers(0, 14),
+       seed=st.integers(0, 5), shuffle=st.booleans())
+def test_pinned_loader_matches_device_shard_and_resumes_anywhere(depth, per_pass, bs, extra, stop, seed, shuffle):
+    """The pinned-host feed (prefetch depth d, in-place shuffles) hands out exactly the batches the device-resident gather draws
+    from the same seed, and a loader restored from `state_dict()` taken after ANY number of batches continues the sequence."""
+    n = bs * per_pass + min(extra, bs - 1)                       # rows beyond the last full batch are never served
+    x = np.arange(n * 2, dtype=np.float32).reshape(n, 2)
+    y = np.arange(n, dtype=np.int64)
+    total = 15
+    want = None
+    if shuffle:                                                   # DeviceShard always permutes: the common reference sequence
+        ds = D.DeviceShard(x, y, bs, "cpu", dtype=torch.float32, shuffle=True, seed=seed)
+        want = [ds.next()[1].clone() for _ in range(total)]
+    mk = lambda: D.PinnedHostLoader(x.copy(), y.copy(), bs, "cpu", shuffle=shuffle, seed=seed, depth=depth)
+    a = mk()
+    got = []
+    for j in range(stop):
+        xb, yb = a.next()
+        assert np.array_equal(xb.numpy(), x[yb.numpy()])
+        got.append(yb.clone())
+    b = mk()
+    b.load_state_dict(a.state_dict())
+    for j in range(stop, total):
+        xb, yb = b.next()
+        assert np.array_equal(xb.numpy(), x[yb.numpy()])
+        got.append(yb.clone())
+    if want is None:
+        want = [torch.arange(bs) + bs * (j % per_pass) for j in range(total)]
+    for j in range(total):
+        assert torch.equal(got[j], want[j]), (j, stop)
